@@ -1,0 +1,208 @@
+/* oracle/ref_shim.cpp — TEST INFRASTRUCTURE ONLY.
+ *
+ * A C-ABI window (for ctypes) onto the UNMODIFIED reference, linked against the
+ * reference objects that oracle/Makefile compiles from /root/reference/src into
+ * oracle/_ref/libvsearch_ref.a.  Nothing here restates an algorithm: every entry
+ * point just marshals plain buffers into the reference's own C++ interface
+ *   search16_init/qprep/search16       (src/core/align_simd.hpp:76-108)
+ *   unique_count                        (src/core/unique.hpp)
+ *   Dbindex::prepare/add_all_sequences  (src/core/dbindex.hpp)
+ *   search_topscores                    (src/core/searchcore.hpp:178)
+ *   search_session_single               (src/core/search.hpp:107)
+ * so that tests can pin oracle/*.c and the CUDA path against the real thing.
+ * The result is oracle/_ref/libvsref.so; it is never linked into the product.
+ */
+#include "vsearch_api.h"
+#include "core/align_simd.hpp"
+#include "core/searchcore.hpp"
+#include "core/search_internal.hpp"
+#include "core/minheap.hpp"
+#include "core/unique.hpp"
+#include "core/mask.hpp"
+
+#include <cstring>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include <memory>
+
+namespace {
+
+struct RefDb {
+  Parameters params;
+  Database db;
+  Dbindex dbindex;
+  bool session = false;
+  int tophits = 0;
+};
+
+void fill_db(Database & db, int n, const char * cat, const int64_t * off, const int * len)
+{
+  db.init();
+  for (int i = 0; i < n; i++) {
+    std::string head = "t" + std::to_string(i);
+    std::string seq(cat + off[i], static_cast<size_t>(len[i]));
+    db.add(false, head.c_str(), seq.c_str(), nullptr, head.size(), seq.size(), 1);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+/* search16 on one query against n targets.  pen[14] is the search16_init argument
+   list in its own order (match, mismatch, 6 opens q_l,t_l,q_i,t_i,q_r,t_r, 6 extensions
+   in the same order) — i.e. ALREADY "open excludes the first extension" as
+   vsearch_apply_defaults_fixups leaves them.  cigars are written NUL-terminated at
+   cigar + i*cigar_stride. */
+int vsref_search16(const int64_t * pen, int n_mismatch,
+                   const char * qseq, int qlen,
+                   int n, const char * tcat, const int64_t * toff, const int * tlen,
+                   short * scores, unsigned short * aligned, unsigned short * matches,
+                   unsigned short * mismatches, unsigned short * gaps,
+                   char * cigar, int64_t cigar_stride)
+{
+  Database db;
+  fill_db(db, n, tcat, toff, tlen);
+  s16info_s * s = search16_init(pen[0], pen[1], pen[2], pen[3], pen[4], pen[5], pen[6], pen[7],
+                                pen[8], pen[9], pen[10], pen[11], pen[12], pen[13],
+                                n_mismatch != 0);
+  std::vector<char> q(qseq, qseq + qlen);
+  q.push_back(0);
+  search16_qprep(s, q.data(), qlen);
+  std::vector<unsigned int> seqnos(static_cast<size_t>(n));
+  for (int i = 0; i < n; i++) { seqnos[static_cast<size_t>(i)] = static_cast<unsigned int>(i); }
+  std::vector<char *> pc(static_cast<size_t>(n), nullptr);
+  search16(s, static_cast<unsigned int>(n), seqnos.data(), scores, aligned, matches,
+           mismatches, gaps, pc.data(), db);
+  int rc = 0;
+  for (int i = 0; i < n; i++) {
+    char * c = pc[static_cast<size_t>(i)];
+    size_t const l = std::strlen(c);
+    if (static_cast<int64_t>(l) + 1 > cigar_stride) { rc = -1; }
+    else { std::memcpy(cigar + i * cigar_stride, c, l + 1); }
+    xfree(c);
+  }
+  search16_exit(s);
+  db.clear();
+  return rc;
+}
+
+/* distinct k-mers of one sequence in first-occurrence order; mask_lower != 0 selects the
+   soft-masking map (Masking::dust / soft), else only non-ACGTU windows are skipped. */
+int vsref_unique_count(int wordlength, const char * seq, int len, int mask_lower,
+                       unsigned int * out, int cap)
+{
+  uhandle_s * uh = unique_init();
+  unsigned int n = 0;
+  unsigned int const * list = nullptr;
+  std::vector<char> s(seq, seq + len);
+  s.push_back(0);
+  unique_count(uh, wordlength, len, s.data(), &n, &list,
+               mask_lower != 0 ? Masking::dust : Masking::none);
+  int const m = static_cast<int>(n) < cap ? static_cast<int>(n) : cap;
+  for (int i = 0; i < m; i++) { out[i] = list[i]; }
+  unique_exit(uh);
+  return static_cast<int>(n);
+}
+
+/* Build a reference Database + Dbindex from plain buffers and open a library session.
+   Only one may exist at a time (the reference serialises sessions, vsearch.cc:283). */
+void * vsref_db_create(int n, const char * cat, const int64_t * off, const int * len,
+                       int wordlength, double id, int maxaccepts, int maxrejects,
+                       int minwordmatches /* <0: default table */, int dust /* 0: qmask/dbmask none */,
+                       int strand_both, int iddef)
+{
+  RefDb * r = new RefDb();
+  Parameters & p = r->params;
+  p.opt_wordlength = wordlength;
+  p.opt_id = id;
+  p.opt_maxaccepts = maxaccepts;
+  p.opt_maxrejects = maxrejects;
+  p.opt_minwordmatches = minwordmatches;
+  p.opt_threads = 1;
+  p.opt_strand = (strand_both != 0);
+  p.opt_iddef = iddef;
+  if (dust == 0) { p.opt_qmask = Masking::none; p.opt_dbmask = Masking::none; }
+  vsearch_session_begin(p);
+  r->session = true;
+  fill_db(r->db, n, cat, off, len);
+  if (p.opt_dbmask == Masking::dust) { dust_all(r->db, p); }
+  r->dbindex.prepare(1, p.opt_dbmask, r->db, p);
+  r->dbindex.add_all_sequences(p.opt_dbmask, r->db, p);
+  int const seqcount = static_cast<int>(r->db.getsequencecount());
+  /* same clamp as search_prep / search_session_init (usearch_global.cpp:598-614) */
+  int64_t th = p.opt_maxaccepts + p.opt_maxrejects + static_cast<int64_t>(MAXDELAYED);
+  if (th > seqcount) { th = seqcount; }
+  r->tophits = static_cast<int>(th);
+  return r;
+}
+
+void vsref_db_free(void * h)
+{
+  RefDb * r = static_cast<RefDb *>(h);
+  r->dbindex.clear();
+  r->db.clear();
+  if (r->session) { vsearch_session_end(); }
+  delete r;
+}
+
+int vsref_db_tophits(void * h) { return static_cast<RefDb *>(h)->tophits; }
+
+/* search_topscores for one (already masked, plus-strand) query: best-first list of
+   (seqno,count,length) exactly as minheap_poplast would hand them out. */
+int vsref_db_topscores(void * h, const char * qseq, int qlen,
+                       unsigned int * seqno, unsigned int * count, unsigned int * length)
+{
+  RefDb * r = static_cast<RefDb *>(h);
+  searchinfo_s si;
+  int const seqcount = static_cast<int>(r->db.getsequencecount());
+  search_thread_init(&si, seqcount, r->tophits, r->params, r->dbindex, r->db);
+  std::vector<char> q(qseq, qseq + qlen);
+  q.push_back(0);
+  si.qsequence = q.data();
+  si.qseqlen = qlen;
+  unique_count(si.uh, static_cast<int>(r->dbindex.wordlength), qlen, q.data(),
+               &si.kmersamplecount, &si.kmersample, r->params.opt_qmask);
+  search_topscores(&si);
+  int n = 0;
+  while (not minheap_isempty(si.m)) {
+    elem_t const e = minheap_poplast(si.m);
+    seqno[n] = e.seqno; count[n] = e.count; length[n] = e.length;
+    ++n;
+  }
+  si.qsequence = nullptr;  /* borrowed */
+  search_thread_exit(&si);
+  return n;
+}
+
+/* search_session_single over a batch of queries (the sequential form of search_batch,
+   search.cpp:511); results[q*max_results + j], fields flattened to plain arrays. */
+void vsref_db_search(void * h, int nq, const char * qcat, const int64_t * qoff, const int * qlen,
+                     int max_results, int * counts,
+                     int * target, double * id, int * matches, int * mismatches, int * gaps,
+                     int * alnlen, int * accepted, int * strand)
+{
+  RefDb * r = static_cast<RefDb *>(h);
+  search_session_s * ss = search_session_alloc();
+  search_session_init(ss, r->params, r->dbindex, r->db);
+  std::vector<search_result_s> res(static_cast<size_t>(max_results));
+  for (int q = 0; q < nq; q++) {
+    std::string seq(qcat + qoff[q], static_cast<size_t>(qlen[q]));
+    std::string head = "q" + std::to_string(q);
+    int c = 0;
+    search_session_single(ss, seq.c_str(), head.c_str(), qlen[q], 1, res.data(), max_results, &c);
+    counts[q] = c;
+    for (int j = 0; j < c; j++) {
+      size_t const o = static_cast<size_t>(q) * static_cast<size_t>(max_results) + static_cast<size_t>(j);
+      search_result_s const & x = res[static_cast<size_t>(j)];
+      target[o] = x.target; id[o] = x.id; matches[o] = x.matches; mismatches[o] = x.mismatches;
+      gaps[o] = x.gaps; alnlen[o] = x.alignment_length; accepted[o] = x.accepted ? 1 : 0;
+      strand[o] = x.strand;
+    }
+  }
+  search_session_cleanup(ss);
+  search_session_free(ss);
+}
+
+}  // extern "C"
