@@ -1,0 +1,166 @@
+/* include/vsg.h — C ABI of libvsg.so, the B200-native (sm_100a CUDA) implementation of the
+ * vsearch hot path: the 16-bit affine-gap global aligner `search16` and the k-mer candidate
+ * ranker `search_topscores`, batched over many queries.
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.  Every entry point
+ * names the reference interface it replaces (reference = torognes/vsearch v2.31.0, paths relative
+ * to its src/).  Errors: functions return 0 on success or a negative VSG_E* code and leave a
+ * message retrievable with vsg_last_error(); nothing throws (the reference is built
+ * -fno-exceptions, Makefile.am:53) and nothing falls back to a CPU path: without a CUDA device
+ * vsg_ctx_create fails with VSG_ENODEVICE.
+ *
+ * In-band "cannot align this pair" is signalled exactly as the reference does it: score ==
+ * VSG_SCORE_SENTINEL (SHRT_MAX), zero statistics, empty CIGAR (core/align_simd.cpp:1463-1479,
+ * 1838-1846, 1871-1881); the caller re-aligns such pairs with its linear-memory aligner
+ * (core/searchcore.cpp:806-832).
+ */
+#ifndef VSG_H
+#define VSG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSG_OK 0
+#define VSG_ENODEVICE (-1) /* no CUDA device / driver */
+#define VSG_ECUDA (-2)     /* a CUDA call failed */
+#define VSG_EINVAL (-3)    /* bad argument */
+#define VSG_ENOMEM (-4)    /* host or device allocation failed */
+#define VSG_ECAP (-5)      /* caller-provided output buffer too small */
+
+#define VSG_SCORE_SENTINEL 32767
+
+typedef struct vsg_ctx vsg_ctx;       /* one per host thread; owns a CUDA stream + scratch  */
+typedef struct vsg_seqset vsg_seqset; /* a set of sequences resident in HBM                 */
+typedef struct vsg_index vsg_index;   /* k-mer postings index resident in HBM               */
+
+/* Scores/penalties in search16_init's own argument order (core/align_simd.hpp:76-91):
+ * v[0]=match v[1]=mismatch, v[2..7]=gap open {query_left,target_left,query_interior,
+ * target_interior,query_right,target_right}, v[8..13]=gap extension in the same order.
+ * "open" excludes the first extension, i.e. the values vsearch_apply_defaults_fixups leaves
+ * in Parameters (vsearch.cc:250-259). */
+typedef struct vsg_scoring {
+  int64_t v[14];
+  int32_t n_mismatch; /* opt_n_mismatch */
+} vsg_scoring;
+
+const char * vsg_last_error(void);
+const char * vsg_version(void);
+/* number of kernels this library has launched in the calling process (bench "gpu_launches") */
+int64_t vsg_launch_count(void);
+
+/* ---- context: replaces search16_init / search16_exit (core/align_simd.cpp:1282-1403) ---- */
+int vsg_ctx_create(int device, const vsg_scoring * scoring, vsg_ctx ** out);
+void vsg_ctx_destroy(vsg_ctx * ctx);
+/* the CUDA stream (cudaStream_t) all work of this context is enqueued on */
+void * vsg_ctx_stream(vsg_ctx * ctx);
+int vsg_ctx_sync(vsg_ctx * ctx);
+
+/* ---- sequences: replaces Database::add / getsequence / getsequencelen
+ *      (core/db.hpp:137-201, core/db.cpp:170-226).  ASCII, one byte per nucleotide, any case,
+ *      IUPAC allowed; offsets index into `cat`. `host` selects where cat/off/len live
+ *      (1 = host memory, copied; 0 = device memory of ctx's device, adopted by reference and
+ *      required to outlive the seqset — used after an NCCL broadcast). ---- */
+int vsg_seqset_create(vsg_ctx * ctx, const char * cat, const int64_t * off, const int32_t * len,
+                      int64_t n, int host, vsg_seqset ** out);
+void vsg_seqset_destroy(vsg_seqset * s);
+int64_t vsg_seqset_count(const vsg_seqset * s);
+
+/* ---- batched alignment: replaces search16_qprep + search16 (core/align_simd.cpp:1406-2060)
+ *      for npairs (query,target) pairs at once.  qidx[i] indexes `queries`, tidx[i] indexes
+ *      `targets`.  Outputs are caller-allocated arrays of npairs elements, identical in meaning
+ *      to search16's pscores/paligned/pmatches/pmismatches/pgaps.
+ *      trims (optional, may be NULL): 4 x int32 per pair {trim_q_left, trim_t_left, trim_q_right,
+ *      trim_t_right} = run length of a leading / trailing D resp. I CIGAR op, before the
+ *      "covers the whole alignment" fix-up of align_trim (core/searchcore.cpp:357-417).
+ *      CIGARs (optional): if cigar_buf != NULL the NUL-terminated CIGAR of pair i is written at
+ *      cigar_buf + cigar_off[i] (cigar_off is an OUTPUT, npairs+1 entries, dense); cigar_cap is
+ *      the buffer size; VSG_ECAP if it does not fit (a capacity of sum(qlen+dlen+1) always fits).
+ *      All pointers are HOST pointers; the sequences themselves are already resident in HBM
+ *      (vsg_seqset_create), only the pair list goes up and the fixed-size results come back. ---- */
+int vsg_align_pairs(vsg_ctx * ctx, const vsg_seqset * queries, const vsg_seqset * targets,
+                    int64_t npairs, const uint32_t * qidx, const uint32_t * tidx,
+                    int16_t * score, uint16_t * aligned, uint16_t * matches,
+                    uint16_t * mismatches, uint16_t * gaps, int32_t * trims,
+                    char * cigar_buf, int64_t cigar_cap, int64_t * cigar_off);
+
+/* Layout of the per-pair statistics record the kernels produce (8 x int32, device side);
+ * exposed so that tools reading the raw buffers agree on it. */
+#define VSG_STAT_SCORE 0
+#define VSG_STAT_ALIGNED 1
+#define VSG_STAT_MATCHES 2
+#define VSG_STAT_MISMATCHES 3
+#define VSG_STAT_GAPS 4
+#define VSG_STAT_TRIM_LEFT 5  /* +run: leading D (gap in target) ; -run: leading I ; 0: leading M */
+#define VSG_STAT_TRIM_RIGHT 6 /* same for the trailing op */
+#define VSG_STAT_CIGARLEN 7   /* strlen of the CIGAR */
+#define VSG_STAT_WORDS 8
+
+/* DP cells (sum qlen*dlen) and kernel time of the forward kernels of the last align call on this
+ * context (cudaEvent, ms) — what bench.py's roofline is computed from. */
+int vsg_last_align_profile(vsg_ctx * ctx, int64_t * cells, float * fwd_ms, float * traceback_ms,
+                           int64_t * fast_pairs, int64_t * exact_pairs);
+
+/* ---- k-mer index: replaces Dbindex::prepare + add_all_sequences + the getters
+ *      (core/dbindex.hpp:79-120, core/dbindex.cpp:121-255).  mask_lower != 0 means soft-masked
+ *      (lower-case) symbols do not seed k-mers (unique.cpp:198-199). ---- */
+int vsg_index_create(vsg_ctx * ctx, const vsg_seqset * db, int wordlength, int mask_lower,
+                     vsg_index ** out);
+void vsg_index_destroy(vsg_index * ix);
+
+/* ---- candidate ranking: replaces unique_count + search_topscores + minheap
+ *      (core/unique.cpp:337-353, core/searchcore.cpp:260-340, core/minheap.cpp) for every query
+ *      of `queries` in [q0, q0+nq).  For query q the best-first list (count desc, target length
+ *      asc, target number asc) of at most tophits targets with count >= min(minwordmatches,
+ *      number of distinct query k-mers) is written to cand_seqno/cand_count[(q-q0)*tophits ...],
+ *      its length to ncand[q-q0].  Host pointers. ---- */
+int vsg_rank(vsg_ctx * ctx, const vsg_index * ix, const vsg_seqset * queries, int64_t q0,
+             int64_t nq, int minwordmatches, int tophits, int mask_lower,
+             uint32_t * cand_seqno, uint32_t * cand_count, int32_t * ncand);
+
+/* ---- whole-path search: replaces search_batch (core/search.hpp:135-145, search.cpp:511-593) /
+ *      the body of search_thread_run (commands/usearch_global.cpp:376-497) for plus-strand (and
+ *      optionally minus-strand) queries with the reference's default pre-alignment filters.
+ *      result layout mirrors search_result_s (core/search.hpp:67-80). ---- */
+typedef struct vsg_search_opts {
+  double id;              /* --id                         */
+  double weak_id;         /* --weak_id (10.0 = default)   */
+  int32_t maxaccepts;     /* --maxaccepts (default 1)     */
+  int32_t maxrejects;     /* --maxrejects (default 32)    */
+  int32_t wordlength;     /* --wordlength (default 8)     */
+  int32_t minwordmatches; /* <0: reference default table  */
+  int32_t iddef;          /* --iddef (default 2)          */
+  int32_t strand_both;    /* --strand both                */
+  int32_t mask_lower;     /* queries are soft-masked      */
+  int32_t reserved;
+} vsg_search_opts;
+
+typedef struct vsg_search_result {
+  int32_t target;
+  int32_t matches;
+  int32_t mismatches;
+  int32_t gaps;
+  int32_t alignment_length;
+  int32_t query_length;
+  int32_t target_length;
+  int32_t accepted;
+  int32_t strand;
+  int32_t nwscore;
+  double id;
+} vsg_search_result;
+
+void vsg_search_opts_default(vsg_search_opts * o);
+/* results[(q)*max_results + j], counts[q]; work (optional, 2 x int64): pairs and DP cells handed
+ * to the aligner — the reference's search16 workload for the same queries. */
+int vsg_search_batch(vsg_ctx * ctx, const vsg_index * ix, const vsg_seqset * db,
+                     const vsg_seqset * queries, int64_t q0, int64_t nq,
+                     const vsg_search_opts * opts, vsg_search_result * results, int max_results,
+                     int32_t * counts, int64_t * work);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSG_H */

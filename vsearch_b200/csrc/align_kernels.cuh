@@ -1,0 +1,572 @@
+// align_kernels.cuh — device code of the batched global aligner (sm_100a).
+//
+// Three kernels replace the reference's search16 (core/align_simd.cpp:1447-2060):
+//
+//  nw_fast_kernel<R,GENERAL>   one WARP aligns one query against TWO targets at once.  Every
+//      32-bit register holds the same DP quantity for both targets as two 16-bit halves
+//      (VIMNMX.S16x2 / VIADD.16x2 are native on sm_100a).  Lane l owns query rows
+//      [l*R, l*R+R) and walks the target columns as an anti-diagonal wavefront: at step s it is at
+//      column s-l, takes H/F of the row above from lane l-1 by warp shuffle and keeps its own H/E
+//      column in registers, so DP state never touches memory.  Substitution scores come from a
+//      shared-memory table (replicated per lane -> conflict free), per-column data (table offset,
+//      target-gap penalties, top-boundary values) from a 64-entry shared-memory ring the warp
+//      refills with coalesced loads every 32 steps.  The four direction bits per cell
+//      (align_simd.cpp:710-717) fall out of the max instructions' predicates and are stored as
+//      R bytes per lane per step, 128*RW contiguous bytes per warp per step.  Queries longer than
+//      32*R rows run as several strips that hand the boundary row over through HBM.
+//      Arithmetic is exact integer arithmetic in a biased 16-bit representation; the host only
+//      sends a pair here when a bound on every intermediate proves that neither saturation nor the
+//      reference's overflow flag can occur (vsg_api.cu: fast_path_ok), in which case the
+//      reference's saturating arithmetic is plain integer arithmetic too.
+//
+//  nw_exact_kernel             one THREAD per pair, 32-bit arithmetic with explicit clamps that
+//      reproduces the reference's saturating 16-bit lanes bit for bit, including the blocks of four
+//      columns, the zero-padded last block and the sticky h_min/h_max overflow flag
+//      (align_simd.cpp:825-826, 1735-1752, 2029-2051).  Used for every pair the bound cannot clear.
+//
+//  traceback_kernel            one thread per pair walks the stored direction bits exactly as
+//      backtrack16 does (align_simd.cpp:1132-1245) and emits statistics, terminal-gap trims and
+//      (optionally) the run-length CIGAR.
+#pragma once
+
+#include "vsg_internal.h"
+
+namespace vsg {
+
+constexpr uint32_t BIAS = 0x4000u;
+constexpr uint32_t BIAS2 = 0x40004000u;
+constexpr int FAST_WARPS = 4;        // warps per CTA
+constexpr int FAST_RMAX = 16;        // rows per lane
+constexpr int RING = 64;             // column records per warp
+
+__host__ __device__ inline int fast_rw(int R) { return R <= 4 ? 1 : (R <= 8 ? 2 : 4); }
+
+__device__ __forceinline__ uint32_t pk2(int lo, int hi)
+{
+  return (static_cast<uint32_t>(lo) & 0xffffu) | (static_cast<uint32_t>(hi) << 16);
+}
+__device__ __forceinline__ uint32_t pk1(int v) { return pk2(v, v); }
+
+// per-halfword signed max; ORs bit_lo / bit_hi into w where b > a strictly (i.e. NOT a >= b)
+__device__ __forceinline__ uint32_t max_flag(uint32_t a, uint32_t b, uint32_t & w,
+                                             uint32_t bit_lo, uint32_t bit_hi)
+{
+  bool ph, pl;
+  uint32_t const m = __vibmax_s16x2(a, b, &ph, &pl);  // VIMNMX.S16x2 with predicate outputs
+  if (!pl) { w |= bit_lo; }
+  if (!ph) { w |= bit_hi; }
+  return m;
+}
+
+__device__ __forceinline__ int code_to_2bit(int c4) { return (c4 == 2) ? 1 : (c4 == 4) ? 2 : (c4 == 8) ? 3 : 0; }
+
+// Semantics self-test of the DPX intrinsic the fast kernel leans on (run once per context).
+// Inputs arrive as kernel arguments so that nothing is folded at compile time.
+__global__ void dpx_selftest_kernel(int * bad, int a0, int a1, int b0, int b1, int c0, int c1, int d0, int d1)
+{
+  bool ph, pl;
+  // halves: lo = (5 vs 7) -> max 7, pred(a>=b)=false ; hi = (9 vs 9) -> pred true
+  uint32_t m = __vibmax_s16x2(pk2(a0, a1), pk2(b0, b1), &ph, &pl);
+  int b = 0;
+  if (m != pk2(7, 9) || pl || !ph) { b |= 1; }
+  // negative halves: lo = (-3 vs -4) -> -3, pred true; hi = (-10 vs 2) -> 2, pred false
+  m = __vibmax_s16x2(pk2(c0, c1), pk2(d0, d1), &ph, &pl);
+  if (m != pk2(-3, 2) || !pl || ph) { b |= 2; }
+  if (__vadd2(pk2(c0, 100), pk2(d1, -7)) != pk2(-1, 93)) { b |= 4; }
+  *bad = b;
+}
+
+template <int R, bool GENERAL>
+__global__ void __launch_bounds__(FAST_WARPS * 32)
+nw_fast_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
+               const FastTask * __restrict__ tasks, int ntasks,
+               uint8_t * __restrict__ dir, uint2 * __restrict__ bnd, int32_t * __restrict__ stats)
+{
+  constexpr int RW = (R <= 4 ? 1 : (R <= 8 ? 2 : 4));
+  constexpr int LUT_WORDS = GENERAL ? 4096 : 64 * 32;
+  __shared__ uint32_t lut[LUT_WORDS];
+  __shared__ uint4 ringA[FAST_WARPS][RING];
+  __shared__ uint32_t ringB[FAST_WARPS][RING];
+
+  int const lane = threadIdx.x & 31;
+  int const wib = threadIdx.x >> 5;
+
+  // substitution table: both halves looked up at once
+  for (int e = threadIdx.x; e < LUT_WORDS; e += blockDim.x) {
+    if (GENERAL) {
+      int const q = e >> 8, dlo = e & 15, dhi = (e >> 4) & 15;
+      lut[e] = pk2(sp.S[dlo][q], sp.S[dhi][q]);
+    } else {
+      int const ent = e >> 5;  // replicated for the 32 lanes: word = ent*32 + lane
+      int const q = 1 << (ent >> 4), dlo = 1 << (ent & 3), dhi = 1 << ((ent >> 2) & 3);
+      lut[e] = pk2(sp.S[dlo][q], sp.S[dhi][q]);
+    }
+  }
+  __syncthreads();
+
+  int const w = blockIdx.x * FAST_WARPS + wib;
+  if (w >= ntasks) { return; }
+  FastTask const tk = tasks[w];
+
+  int const Q = qs.len[tk.q];
+  uint8_t const * __restrict__ qsym = qs.sym + qs.off[tk.q];
+  int const Dlo = ts.len[tk.tlo], Dhi = ts.len[tk.thi];
+  uint8_t const * __restrict__ dlo_p = ts.sym + ts.off[tk.tlo];
+  uint8_t const * __restrict__ dhi_p = ts.sym + ts.off[tk.thi];
+  int const dmax = tk.dmax;
+  int const nsteps = dmax + 31;
+  int const strip_rows = 32 * R;
+  int const nstrips = (Q + strip_rows - 1) / strip_rows;
+  size_t const strip_bytes = static_cast<size_t>(nsteps) * 32 * RW * 4;
+
+  int const QRqi = sp.go[Q_I] + sp.ge[Q_I], Rqi = sp.ge[Q_I];
+  int const QRqr = sp.go[Q_R] + sp.ge[Q_R], Rqr = sp.ge[Q_R];
+  int const QRti = sp.go[T_I] + sp.ge[T_I], Rti = sp.ge[T_I];
+  int const QRtr = sp.go[T_R] + sp.ge[T_R], Rtr = sp.ge[T_R];
+  int const gotl = sp.go[T_L], getl = sp.ge[T_L];
+  int const goql = sp.go[Q_L], geql = sp.ge[Q_L];
+
+  // where the final score H(Q-1, D-1) lives
+  int const klast = (Q - 1) / strip_rows;
+  int const llast = ((Q - 1) % strip_rows) / R;
+  int const rlast = (Q - 1) % R;
+  int score_lo = 0, score_hi = 0;
+
+  uint4 * const rA = ringA[wib];
+  uint32_t * const rB = ringB[wib];
+  uint2 * const mybnd = bnd + tk.bnd_off;
+  uint8_t const * const lutb = reinterpret_cast<uint8_t const *>(lut);
+
+  for (int strip = 0; strip < nstrips; strip++) {
+    int const row0 = strip * strip_rows + lane * R;
+
+    uint32_t Hl[R], E[R], rowoff[R], QRq[R], Rq[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      int const i = row0 + r;
+      int const code = (i < Q) ? (qsym[i] & 15) : 0;
+      rowoff[r] = GENERAL ? static_cast<uint32_t>(code) * 1024u
+                          : (static_cast<uint32_t>(code_to_2bit(code)) * 16u * 32u + lane) * 4u;
+      bool const last = (i == Q - 1);
+      QRq[r] = pk1(last ? QRqr : QRqi);
+      Rq[r] = pk1(last ? Rqr : Rqi);
+      Hl[r] = BIAS2 - pk1(gotl + (i + 1) * getl);  // H(i,-1)     (align_simd.cpp:852-853)
+      E[r] = Hl[r] - QRq[r];                       // E(i,0)      (align_simd.cpp:855-857)
+    }
+    // H(row0-1,-1): the diagonal input of this lane's first row at column 0
+    uint32_t diag_in = (row0 == 0) ? BIAS2 : BIAS2 - pk1(gotl + row0 * getl);
+    uint32_t Hout = BIAS2, Fout = BIAS2;
+    uint8_t * const dstrip = dir + tk.dir_off + static_cast<size_t>(strip) * strip_bytes;
+    bool const write_bnd = (strip + 1 < nstrips) && (lane == 31);
+
+    for (int s = 0; s < nsteps; s++) {
+      if ((s & 31) == 0) {
+        // refill the ring with columns [s, s+32): one column per lane, coalesced
+        __syncwarp();
+        int const cc = s + lane;
+        if (cc < dmax) {
+          int const a = (cc < Dlo) ? (dlo_p[cc] & 15) : 0;
+          int const b = (cc < Dhi) ? (dhi_p[cc] & 15) : 0;
+          uint4 rec;
+          rec.x = GENERAL ? static_cast<uint32_t>(a + 16 * b) * 4u
+                          : static_cast<uint32_t>(code_to_2bit(a) + 4 * code_to_2bit(b)) * 128u;
+          // target-gap penalties: right-end values from the target's last column on
+          // (align_simd.cpp:1741-1751)
+          rec.y = pk2(cc >= Dlo - 1 ? QRtr : QRti, cc >= Dhi - 1 ? QRtr : QRti);
+          rec.z = pk2(cc >= Dlo - 1 ? Rtr : Rti, cc >= Dhi - 1 ? Rtr : Rti);
+          uint32_t fin;
+          if (strip == 0) {
+            rec.w = BIAS2 - pk1(goql + (cc + 1) * geql);  // H(-1,c)  (align_simd.cpp:1895-1901)
+            fin = rec.w - rec.y;                          // F(0,c)   (align_simd.cpp:830-833)
+          } else {
+            uint2 const v = __ldcg(mybnd + cc);
+            rec.w = v.x;
+            fin = v.y;
+          }
+          rA[cc & (RING - 1)] = rec;
+          rB[cc & (RING - 1)] = fin;
+        }
+        __syncwarp();
+      }
+
+      uint32_t hin = __shfl_up_sync(0xffffffffu, Hout, 1);
+      uint32_t fin = __shfl_up_sync(0xffffffffu, Fout, 1);
+      int const c = s - lane;
+      if (c >= 0 && c < dmax) {
+        uint4 const rec = rA[c & (RING - 1)];
+        if (lane == 0) { hin = rec.w; fin = rB[c & (RING - 1)]; }
+
+        uint32_t F = fin;
+        uint32_t diag = diag_in;
+        uint32_t wd[RW];
+#pragma unroll
+        for (int k = 0; k < RW; k++) { wd[k] = 0; }
+
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          uint32_t const sh = 8u * (r & 3);
+          uint32_t & wr = wd[r >> 2];
+          uint32_t const S = *reinterpret_cast<uint32_t const *>(lutb + rowoff[r] + rec.x);
+          uint32_t const t = __vadd2(diag, S);                         // H(i-1,j-1) + S
+          uint32_t const m1 = max_flag(t, F, wr, 1u << sh, 16u << sh);  // up:   F > h
+          uint32_t const h = max_flag(m1, E[r], wr, 2u << sh, 32u << sh);  // left: E > h
+          diag = Hl[r];
+          Hl[r] = h;
+          uint32_t const hf = h - rec.y;                               // H - QR_t
+          uint32_t const f = F - rec.z;                                // F - R_t
+          F = max_flag(hf, f, wr, 4u << sh, 64u << sh);                // extup:   f > hf
+          uint32_t const he = h - QRq[r];
+          uint32_t const e = E[r] - Rq[r];
+          E[r] = max_flag(he, e, wr, 8u << sh, 128u << sh);            // extleft: e > he
+        }
+        Hout = Hl[R - 1];
+        Fout = F;
+        diag_in = hin;
+
+        uint32_t * const dp = reinterpret_cast<uint32_t *>(dstrip) + (static_cast<size_t>(s) * 32 + lane) * RW;
+        if (RW == 1) { dp[0] = wd[0]; }
+        else if (RW == 2) { *reinterpret_cast<uint2 *>(dp) = make_uint2(wd[0], wd[1]); }
+        else { *reinterpret_cast<uint4 *>(dp) = make_uint4(wd[0], wd[1], wd[RW > 2 ? 2 : 0], wd[RW > 3 ? 3 : 0]); }
+
+        if (write_bnd) { __stcg(mybnd + c, make_uint2(Hout, Fout)); }
+
+        if (strip == klast && lane == llast && (c == Dlo - 1 || c == Dhi - 1)) {
+          uint32_t v = 0;
+#pragma unroll
+          for (int r = 0; r < R; r++) { if (r == rlast) { v = Hl[r]; } }
+          if (c == Dlo - 1) { score_lo = static_cast<int>(v & 0xffffu) - static_cast<int>(BIAS); }
+          if (c == Dhi - 1) { score_hi = static_cast<int>(v >> 16) - static_cast<int>(BIAS); }
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  if (lane == llast) {
+    if (tk.out_lo >= 0) { stats[static_cast<size_t>(tk.out_lo) * VSG_STAT_WORDS + VSG_STAT_SCORE] = score_lo; }
+    if (tk.out_hi >= 0) { stats[static_cast<size_t>(tk.out_hi) * VSG_STAT_WORDS + VSG_STAT_SCORE] = score_hi; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact kernel: bit-for-bit model of one saturating 16-bit lane, one thread per pair
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sat16(int x) { return x > 32767 ? 32767 : (x < -32768 ? -32768 : x); }
+
+__global__ void nw_exact_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
+                                const ExactTask * __restrict__ tasks, int ntasks,
+                                uint8_t * __restrict__ dir, int16_t * __restrict__ he,
+                                int32_t * __restrict__ stats)
+{
+  int const w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= ntasks) { return; }
+  ExactTask const tk = tasks[w];
+  int const Q = qs.len[tk.q];
+  int const D = ts.len[tk.t];
+  uint8_t const * __restrict__ qsym = qs.sym + qs.off[tk.q];
+  uint8_t const * __restrict__ dsym = ts.sym + ts.off[tk.t];
+  uint8_t * __restrict__ dp = dir + tk.dir_off;
+  int16_t * __restrict__ Hcol = he + tk.he_off;
+  int16_t * __restrict__ Ecol = Hcol + Q;
+
+  int const QRqi = sp.go[Q_I] + sp.ge[Q_I], Rqi = sp.ge[Q_I];
+  int const QRqr = sp.go[Q_R] + sp.ge[Q_R], Rqr = sp.ge[Q_R];
+  int const QRti = sp.go[T_I] + sp.ge[T_I], Rti = sp.ge[T_I];
+  int const QRtr = sp.go[T_R] + sp.ge[T_R], Rtr = sp.ge[T_R];
+  int const QRtl = sp.go[T_L] + sp.ge[T_L], Rtl = sp.ge[T_L];
+  int const Rql = sp.ge[Q_L];
+
+  int H[4], F[4], Sm[4] = {0, 0, 0, 0};
+  H[0] = 0;
+  for (int k = 1; k < 4; k++) { H[k] = static_cast<int16_t>(-sp.go[Q_L] - k * sp.ge[Q_L]); }
+  for (int k = 0; k < 4; k++) { F[k] = static_cast<int16_t>(-sp.go[Q_L] - (k + 1) * sp.ge[Q_L]); }
+
+  bool overflow = false;
+  int const nblocks = (D + 3) / 4;
+  for (int b = 0; b < nblocks; b++) {
+    int sym[4], QRt[4], Rt[4], h[4], f[4], n[4] = {0, 0, 0, 0};
+    bool const ends = (4 * b + 4 >= D);
+    for (int k = 0; k < 4; k++) {
+      int const j = 4 * b + k;
+      sym[k] = j < D ? (dsym[j] & 15) : 0;
+      bool const right = ends && (k >= ((D + 3) & 3));
+      QRt[k] = right ? sat16(QRti + sat16(QRtr - QRti)) : QRti;
+      Rt[k] = right ? sat16(Rti + sat16(Rtr - Rti)) : Rti;
+      h[k] = H[k];
+      f[k] = sat16(F[k] - QRt[k]);
+    }
+    int h_min = 0, h_max = 0;
+    int M = QRtl;
+    for (int i = 0; i < Q; i++) {
+      bool const last = (i == Q - 1);
+      int h4 = 0, E;
+      if (b == 0) {
+        if (!last) {
+          h4 = sat16(0 - M);
+          E = sat16(sat16(0 - M) - QRqi);
+          M = sat16(M + Rtl);
+        } else {
+          E = sat16(sat16(0 - M) - QRqr);
+        }
+      } else {
+        if (!last) { h4 = Hcol[i]; }
+        E = Ecol[i];
+      }
+      int const QRq = last ? QRqr : QRqi;
+      int const Rq = last ? Rqr : Rqi;
+      int const qc = qsym[i] & 15;
+      for (int k = 0; k < 4; k++) {
+        int Hc = sat16(h[k] + sp.S[sym[k]][qc]);
+        int bits = 0;
+        if (f[k] > Hc) { bits |= 1; }
+        Hc = max(Hc, f[k]);
+        if (E > Hc) { bits |= 2; }
+        Hc = max(Hc, E);
+        h_min = min(h_min, Hc);
+        h_max = max(h_max, Hc);
+        n[k] = Hc;
+        int const HF = sat16(Hc - QRt[k]);
+        f[k] = sat16(f[k] - Rt[k]);
+        if (f[k] > HF) { bits |= 4; }
+        f[k] = max(f[k], HF);
+        int const HE = sat16(Hc - QRq);
+        E = sat16(E - Rq);
+        if (E > HE) { bits |= 8; }
+        E = max(E, HE);
+        int const j = 4 * b + k;
+        if (j < D) { dp[static_cast<size_t>(i) * D + j] = static_cast<uint8_t>(bits); }
+      }
+      Hcol[i] = static_cast<int16_t>(n[3]);
+      Ecol[i] = static_cast<int16_t>(E);
+      h[0] = h4; h[1] = n[0]; h[2] = n[1]; h[3] = n[2];
+    }
+    for (int k = 0; k < 4; k++) { Sm[k] = n[k]; }
+    if (h_min <= sp.score_min || h_max >= 32767) { overflow = true; }
+    H[0] = sat16(H[3] - Rql); H[1] = sat16(H[0] - Rql); H[2] = sat16(H[1] - Rql); H[3] = sat16(H[2] - Rql);
+    F[0] = sat16(F[3] - Rql); F[1] = sat16(F[0] - Rql); F[2] = sat16(F[1] - Rql); F[3] = sat16(F[2] - Rql);
+  }
+  stats[static_cast<size_t>(tk.out) * VSG_STAT_WORDS + VSG_STAT_SCORE] =
+      overflow ? VSG_SCORE_SENTINEL : Sm[(D + 3) & 3];
+}
+
+// ---------------------------------------------------------------------------------------------
+// traceback (backtrack16, align_simd.cpp:1132-1245) + trims + optional CIGAR text
+// ---------------------------------------------------------------------------------------------
+struct DirReader {
+  uint8_t const * base;
+  int kind, R, RW, half, D;
+  size_t strip_bytes;
+  int strip_rows;
+  __device__ __forceinline__ int get(int i, int j) const
+  {
+    if (kind == 1) { return base[static_cast<size_t>(i) * D + j]; }
+    int const strip = i / strip_rows;
+    int const il = i - strip * strip_rows;
+    int const l = il / R;
+    int const r = il - l * R;
+    size_t const a = static_cast<size_t>(strip) * strip_bytes +
+                     (static_cast<size_t>(j + l) * 32 + l) * (RW * 4) + r;
+    int const v = base[a];
+    return half ? (v >> 4) : (v & 15);
+  }
+};
+
+struct CigarWriter {
+  char * end;   // next byte is written at --end
+  char op;
+  int run;
+  int len;
+  bool text;
+  __device__ __forceinline__ void flush()
+  {
+    if (op != 0 && run != 0) {
+      int n = 1;
+      if (text) { *--end = op; }
+      if (run > 1) {
+        int v = run;
+        while (v > 0) {
+          if (text) { *--end = static_cast<char>('0' + (v % 10)); }
+          v /= 10;
+          n++;
+        }
+      }
+      len += n;
+    }
+  }
+  __device__ __forceinline__ void push(char o)
+  {
+    if (o == op) { run++; return; }
+    flush();
+    op = o;
+    run = 1;
+  }
+};
+
+template <bool TEXT>
+__global__ void traceback_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
+                                 const PairDesc * __restrict__ pairs, int npairs,
+                                 uint8_t const * __restrict__ dir, char * __restrict__ cigar_scratch,
+                                 int32_t * __restrict__ stats)
+{
+  int const p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) { return; }
+  PairDesc const pd = pairs[p];
+  int32_t * const st = stats + static_cast<size_t>(pd.out) * VSG_STAT_WORDS;
+  if (st[VSG_STAT_SCORE] == VSG_SCORE_SENTINEL) {
+    st[VSG_STAT_ALIGNED] = 0; st[VSG_STAT_MATCHES] = 0; st[VSG_STAT_MISMATCHES] = 0;
+    st[VSG_STAT_GAPS] = 0; st[VSG_STAT_TRIM_LEFT] = 0; st[VSG_STAT_TRIM_RIGHT] = 0;
+    st[VSG_STAT_CIGARLEN] = 0;
+    if (TEXT) { cigar_scratch[pd.cigar_off] = 0; }
+    return;
+  }
+  int const Q = qs.len[pd.q];
+  int const D = ts.len[pd.t];
+  uint8_t const * __restrict__ qsym = qs.sym + qs.off[pd.q];
+  uint8_t const * __restrict__ dsym = ts.sym + ts.off[pd.t];
+
+  DirReader rd;
+  rd.base = dir + pd.dir_off;
+  rd.kind = pd.kind; rd.R = pd.R; rd.RW = fast_rw(pd.R); rd.half = pd.half; rd.D = D;
+  rd.strip_rows = 32 * pd.R;
+  rd.strip_bytes = static_cast<size_t>(pd.dmax + 31) * 32 * rd.RW * 4;
+
+  CigarWriter cw;
+  cw.text = TEXT;
+  cw.end = TEXT ? (cigar_scratch + pd.cigar_off + Q + D + 1) : nullptr;
+  if (TEXT) { *--cw.end = 0; }
+  cw.op = 0; cw.run = 0; cw.len = 0;
+
+  int aligned = 0, matches = 0, mismatches = 0, gaps = 0;
+  int i = Q - 1, j = D - 1;
+  char op = 0;
+  int last_run_op = 0;  // op of the run that ends the alignment (first one pushed)
+  int last_run = 0;
+  bool first_run_open = true;
+
+  while (i >= 0 && j >= 0) {
+    aligned++;
+    int const b = rd.get(i, j);
+    char nop;
+    if (op == 'I' && (b & 8)) { j--; nop = 'I'; }
+    else if (op == 'D' && (b & 4)) { i--; nop = 'D'; }
+    else if (b & 2) { if (op != 'I') { gaps++; } j--; nop = 'I'; }
+    else if (b & 1) { if (op != 'D') { gaps++; } i--; nop = 'D'; }
+    else {
+      int const a = qsym[i] & 15, c = dsym[j] & 15;
+      if ((a & c) != 0) {
+        if (sp.n_mismatch && (a == 15 || c == 15)) { mismatches++; } else { matches++; }
+      } else { mismatches++; }
+      i--; j--; nop = 'M';
+    }
+    if (first_run_open) {
+      if (last_run == 0 || nop == last_run_op) { last_run_op = nop; last_run++; }
+      else { first_run_open = false; }
+    }
+    cw.push(nop);
+    op = nop;
+  }
+  while (i >= 0) {
+    aligned++;
+    if (op != 'D') { gaps++; }
+    i--;
+    if (first_run_open) {
+      if (last_run == 0 || last_run_op == 'D') { last_run_op = 'D'; last_run++; }
+      else { first_run_open = false; }
+    }
+    cw.push('D');
+    op = 'D';
+  }
+  while (j >= 0) {
+    aligned++;
+    if (op != 'I') { gaps++; }
+    j--;
+    if (first_run_open) {
+      if (last_run == 0 || last_run_op == 'I') { last_run_op = 'I'; last_run++; }
+      else { first_run_open = false; }
+    }
+    cw.push('I');
+    op = 'I';
+  }
+  // the run still open in the writer is the alignment's FIRST (leftmost) run
+  int const first_op = cw.op, first_run = cw.run;
+  cw.flush();
+
+  st[VSG_STAT_ALIGNED] = aligned;
+  st[VSG_STAT_MATCHES] = matches;
+  st[VSG_STAT_MISMATCHES] = mismatches;
+  st[VSG_STAT_GAPS] = gaps;
+  st[VSG_STAT_TRIM_LEFT] = first_op == 'D' ? first_run : (first_op == 'I' ? -first_run : 0);
+  st[VSG_STAT_TRIM_RIGHT] = last_run_op == 'D' ? last_run : (last_run_op == 'I' ? -last_run : 0);
+  st[VSG_STAT_CIGARLEN] = cw.len;
+  // the text (if any) sits right-aligned: it ends with its NUL at region + Q + D
+}
+
+// CIGAR texts sit right-aligned in their scratch regions; pack them densely (NUL-terminated)
+__global__ void cigar_gather_kernel(const PairDesc * __restrict__ pairs, int npairs, DevSeqs qs,
+                                    DevSeqs ts, const int32_t * __restrict__ stats,
+                                    const int64_t * __restrict__ dense_off,
+                                    const char * __restrict__ scratch, char * __restrict__ dense)
+{
+  int const p = blockIdx.x;
+  if (p >= npairs) { return; }
+  PairDesc const pd = pairs[p];
+  int const len = stats[static_cast<size_t>(pd.out) * VSG_STAT_WORDS + VSG_STAT_CIGARLEN];
+  char * const dst = dense + dense_off[p];
+  if (len == 0) {
+    if (threadIdx.x == 0) { dst[0] = 0; }
+    return;
+  }
+  int const Q = qs.len[pd.q], D = ts.len[pd.t];
+  char const * const src = scratch + pd.cigar_off + (Q + D) - len;
+  for (int k = threadIdx.x; k <= len; k += blockDim.x) { dst[k] = src[k]; }
+}
+
+__global__ void cigar_len_kernel(const PairDesc * __restrict__ pairs, const int32_t * __restrict__ stats,
+                                 int npairs, int64_t * __restrict__ lens)
+{
+  int const p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < npairs) {
+    lens[p] = stats[static_cast<size_t>(pairs[p].out) * VSG_STAT_WORDS + VSG_STAT_CIGARLEN] + 1;
+  }
+}
+
+// ASCII -> symbol byte (4-bit code | lower-case flag), per-sequence non-ACGTU flag
+__device__ __forceinline__ int ascii_to_code(int c)
+{
+  int const u = (c >= 'a' && c <= 'z') ? c - 32 : c;
+  switch (u) {
+    case 'A': return 1; case 'C': return 2; case 'G': return 4; case 'T': case 'U': return 8;
+    case 'M': return 3; case 'R': return 5; case 'S': return 6; case 'V': return 7;
+    case 'W': return 9; case 'Y': return 10; case 'H': return 11; case 'K': return 12;
+    case 'D': return 13; case 'B': return 14; case 'N': return 15;
+    default: return 0;
+  }
+}
+
+__global__ void encode_kernel(const char * __restrict__ ascii, uint8_t * __restrict__ sym, int64_t total)
+{
+  int64_t const i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < total) {
+    int const c = static_cast<unsigned char>(ascii[i]);
+    int const lower = (c >= 'a' && c <= 'z') ? 16 : 0;
+    sym[i] = static_cast<uint8_t>(ascii_to_code(c) | lower);
+  }
+}
+
+__global__ void nonacgt_kernel(DevSeqs s, uint8_t * __restrict__ flag)
+{
+  int64_t const w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  int const lane = threadIdx.x & 31;
+  if (w >= s.n) { return; }
+  uint8_t const * p = s.sym + s.off[w];
+  int const n = s.len[w];
+  int bad = 0;
+  for (int i = lane; i < n; i += 32) {
+    int const c = p[i] & 15;
+    bad |= !(c == 1 || c == 2 || c == 4 || c == 8);
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane == 0) { flag[w] = static_cast<uint8_t>(bad); }
+}
+
+}  // namespace vsg

@@ -1,0 +1,669 @@
+// vsg_api.cu — host side of libvsg.so: contexts, sequence sets in HBM, and the batched aligner
+// entry point vsg_align_pairs (replaces search16_init/qprep/search16/exit,
+// reference core/align_simd.cpp:1282-2060; see include/vsg.h for the per-function mapping).
+#include "align_kernels.cuh"
+
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
+namespace vsg {
+
+static thread_local std::string g_last_error;
+void Error::set(const std::string & m) { g_last_error = m; }
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int DevBuf::reserve(size_t bytes)
+{
+  if (bytes <= cap) { return VSG_OK; }
+  if (p != nullptr) { cudaFree(p); p = nullptr; cap = 0; }
+  size_t const want = bytes + bytes / 8 + 256;
+  cudaError_t const e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    p = nullptr;
+    Error::set(std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+    return VSG_ENOMEM;
+  }
+  cap = want;
+  return VSG_OK;
+}
+void DevBuf::release() { if (p != nullptr) { cudaFree(p); p = nullptr; cap = 0; } }
+
+int PinBuf::reserve(size_t bytes)
+{
+  if (bytes <= cap) { return VSG_OK; }
+  if (p != nullptr) { cudaFreeHost(p); p = nullptr; cap = 0; }
+  size_t const want = bytes + bytes / 8 + 256;
+  cudaError_t const e = cudaMallocHost(&p, want);
+  if (e != cudaSuccess) {
+    p = nullptr;
+    Error::set(std::string("cudaMallocHost(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+    return VSG_ENOMEM;
+  }
+  cap = want;
+  return VSG_OK;
+}
+void PinBuf::release() { if (p != nullptr) { cudaFreeHost(p); p = nullptr; cap = 0; } }
+
+// ---- scoring ---------------------------------------------------------------------------------
+static int16_t clamp_cell(int64_t v, int64_t limit, bool & fb)
+{
+  if (v > limit) { fb = true; return static_cast<int16_t>(limit); }
+  if (v < -limit) { fb = true; return static_cast<int16_t>(-limit); }
+  return static_cast<int16_t>(v);
+}
+
+static bool ambiguous4(unsigned c) { return !(c == 1 || c == 2 || c == 4 || c == 8); }
+
+static void build_score_params(const vsg_scoring & s, ScoreParams & p)
+{
+  bool fb = false;
+  int64_t const slim = 32767, plim = 32767 / 5;  // align_simd.cpp:1256-1257
+  p.match = clamp_cell(s.v[0], slim, fb);
+  p.mismatch = clamp_cell(s.v[1], slim, fb);
+  for (int k = 0; k < 6; k++) {
+    p.go[k] = clamp_cell(s.v[2 + k], plim, fb);
+    p.ge[k] = clamp_cell(s.v[8 + k], plim, fb);
+  }
+  p.n_mismatch = s.n_mismatch != 0 ? 1 : 0;
+  p.fallback = fb ? 1 : 0;
+  for (unsigned i = 0; i < 16; i++) {
+    for (unsigned j = 0; j < 16; j++) {
+      int16_t v;
+      if (p.n_mismatch && (i == 15 || j == 15)) { v = p.mismatch; }
+      else if (ambiguous4(i) || ambiguous4(j)) { v = 0; }
+      else if (i == j) { v = p.match; }
+      else { v = p.mismatch; }
+      p.S[i][j] = v;
+    }
+  }
+  int gpmax = 0;
+  for (int k = 0; k < 6; k++) { gpmax = std::max(gpmax, p.go[k] + p.ge[k]); }
+  p.score_min = static_cast<int16_t>(-32768 + gpmax);  // align_simd.cpp:1432-1444
+}
+
+// search16_fits, align_simd.cpp:130-134
+static inline bool fits16(int64_t q, int64_t d) { return (q + d <= 65535) && (q * d <= 25000000LL); }
+
+// Rows per lane and strip count for a query of length Q.
+static inline void fast_shape(int Q, bool general, int & R, int & nstrips)
+{
+  nstrips = (Q + 32 * FAST_RMAX - 1) / (32 * FAST_RMAX);
+  R = (Q + 32 * nstrips - 1) / (32 * nstrips);
+  if (R < 1) { R = 1; }
+  if (general) { R = R <= 4 ? 4 : (R <= 8 ? 8 : 16); }
+  nstrips = (Q + 32 * R - 1) / (32 * R);
+}
+
+// Can the biased 16-bit wavefront kernel represent every intermediate of a (Qpad x D) problem
+// exactly, and is the reference's overflow flag provably silent?  Bounds (penalties >= 0):
+//   every H, incl. both boundaries and the reference's <= 3 padding columns, is
+//     >= -(G + Qpad*Rm) - G - (D+4)*Rm            (left column, then one gap along the row)
+//     <= Smax * min(Qpad, D+4)
+//   E, F and the temporaries (h-QR, e-R, diag+S) stay within 2G+|Smin| below / Smax above that.
+static bool fast_path_ok(const ScoreParams & sp, int Qpad, int D)
+{
+  int G = 0, Rm = 0;
+  for (int k = 0; k < 6; k++) {
+    if (sp.go[k] < 0 || sp.ge[k] < 0) { return false; }
+    G = std::max(G, sp.go[k] + sp.ge[k]);
+    Rm = std::max<int>(Rm, sp.ge[k]);
+  }
+  int64_t smax = 0, smin = 0;
+  for (int i = 0; i < 16; i++) {
+    for (int j = 0; j < 16; j++) {
+      smax = std::max<int64_t>(smax, sp.S[i][j]);
+      smin = std::min<int64_t>(smin, sp.S[i][j]);
+    }
+  }
+  int64_t const lb = -(static_cast<int64_t>(G) + static_cast<int64_t>(Qpad) * Rm) - G -
+                     static_cast<int64_t>(D + 4) * Rm - 2LL * G + smin;
+  int64_t const ub = smax * std::min<int64_t>(Qpad, D + 4) + smax;
+  return lb > -16000 && ub < 16000;
+}
+
+}  // namespace vsg
+
+using namespace vsg;
+
+// ---- misc C ABI ------------------------------------------------------------------------------
+extern "C" const char * vsg_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char * vsg_version(void) { return "vsearch_b200 0.1 (sm_100a)"; }
+extern "C" int64_t vsg_launch_count(void) { return g_launches.load(); }
+
+// ---- context ---------------------------------------------------------------------------------
+extern "C" int vsg_ctx_create(int device, const vsg_scoring * scoring, vsg_ctx ** out)
+{
+  if (out == nullptr || scoring == nullptr) { Error::set("vsg_ctx_create: null argument"); return VSG_EINVAL; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    Error::set(std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+               " (libvsg has no CPU fallback)");
+    return VSG_ENODEVICE;
+  }
+  if (device < 0 || device >= ndev) { Error::set("vsg_ctx_create: bad device ordinal"); return VSG_EINVAL; }
+  VSG_CUDA_OK(cudaSetDevice(device));
+  vsg_ctx * c = new (std::nothrow) vsg_ctx();
+  if (c == nullptr) { Error::set("out of host memory"); return VSG_ENOMEM; }
+  c->device = device;
+  c->scoring = *scoring;
+  build_score_params(*scoring, c->sp);
+  const char * df = std::getenv("VSG_DISABLE_FAST");
+  c->fast_disabled = (df != nullptr && df[0] == '1');
+  const char * db = std::getenv("VSG_DIR_BUDGET_MB");
+  if (db != nullptr && std::atoll(db) > 0) { c->dir_budget = static_cast<size_t>(std::atoll(db)) << 20; }
+  VSG_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (auto & ev : c->ev) { VSG_CUDA_OK(cudaEventCreate(&ev)); }
+  // the fast kernel leans on VIMNMX.S16x2 predicate semantics: check them on this device once
+  int * d_bad = nullptr;
+  VSG_CUDA_OK(cudaMalloc(&d_bad, sizeof(int)));
+  dpx_selftest_kernel<<<1, 1, 0, c->stream>>>(d_bad, 5, 9, 7, 9, -3, -10, -4, 2);
+  count_launch();
+  int bad = -1;
+  VSG_CUDA_OK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_bad);
+  if (bad != 0) {
+    Error::set("DPX self-test failed (code " + std::to_string(bad) + "): __vibmax_s16x2/__vadd2 semantics differ");
+    vsg_ctx_destroy(c);
+    return VSG_ECUDA;
+  }
+  *out = c;
+  return VSG_OK;
+}
+
+extern "C" void vsg_ctx_destroy(vsg_ctx * c)
+{
+  if (c == nullptr) { return; }
+  cudaSetDevice(c->device);
+  if (c->stream != nullptr) { cudaStreamSynchronize(c->stream); }
+  for (DevBuf * b : {&c->dir, &c->bnd, &c->he, &c->cigar_scratch, &c->cigar_dense, &c->stats,
+                     &c->tasks_fast, &c->tasks_exact, &c->pairs, &c->cigar_len, &c->cigar_offs,
+                     &c->cub_tmp, &c->rank_tmp}) { b->release(); }
+  for (PinBuf * b : {&c->h_tasks, &c->h_stats, &c->h_pairs, &c->h_misc}) { b->release(); }
+  for (auto & ev : c->ev) { if (ev != nullptr) { cudaEventDestroy(ev); } }
+  if (c->stream != nullptr) { cudaStreamDestroy(c->stream); }
+  delete c;
+}
+
+extern "C" void * vsg_ctx_stream(vsg_ctx * c) { return c != nullptr ? static_cast<void *>(c->stream) : nullptr; }
+
+extern "C" int vsg_ctx_sync(vsg_ctx * c)
+{
+  if (c == nullptr) { return VSG_EINVAL; }
+  VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return VSG_OK;
+}
+
+// ---- sequence sets ---------------------------------------------------------------------------
+extern "C" int vsg_seqset_create(vsg_ctx * c, const char * cat, const int64_t * off, const int32_t * len,
+                                 int64_t n, int host, vsg_seqset ** out)
+{
+  if (c == nullptr || out == nullptr || n < 0 || (n > 0 && (cat == nullptr || off == nullptr || len == nullptr))) {
+    Error::set("vsg_seqset_create: bad argument");
+    return VSG_EINVAL;
+  }
+  *out = nullptr;
+  VSG_CUDA_OK(cudaSetDevice(c->device));
+  vsg_seqset * s = new (std::nothrow) vsg_seqset();
+  if (s == nullptr) { Error::set("out of host memory"); return VSG_ENOMEM; }
+  s->device = c->device;
+  s->h_len.resize(static_cast<size_t>(n));
+  std::vector<int64_t> h_off(static_cast<size_t>(n));
+  if (host != 0) {
+    if (n > 0) {
+      std::memcpy(s->h_len.data(), len, sizeof(int32_t) * static_cast<size_t>(n));
+      std::memcpy(h_off.data(), off, sizeof(int64_t) * static_cast<size_t>(n));
+    }
+  } else if (n > 0) {
+    VSG_CUDA_OK(cudaMemcpyAsync(s->h_len.data(), len, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    VSG_CUDA_OK(cudaMemcpyAsync(h_off.data(), off, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+  }
+  int64_t total = 0;
+  for (int64_t i = 0; i < n; i++) {
+    if (s->h_len[i] < 0 || h_off[i] < 0) { delete s; Error::set("vsg_seqset_create: negative length/offset"); return VSG_EINVAL; }
+    total = std::max<int64_t>(total, h_off[i] + s->h_len[i]);
+  }
+  s->total = total;
+  int rc;
+  if ((rc = s->b_sym.reserve(static_cast<size_t>(total) + 64)) != VSG_OK ||
+      (rc = s->b_off.reserve(sizeof(int64_t) * static_cast<size_t>(n) + 8)) != VSG_OK ||
+      (rc = s->b_len.reserve(sizeof(int32_t) * static_cast<size_t>(n) + 8)) != VSG_OK) {
+    vsg_seqset_destroy(s);
+    return rc;
+  }
+  const char * d_ascii = cat;
+  DevBuf tmp_ascii;
+  if (host != 0 && total > 0) {
+    if ((rc = tmp_ascii.reserve(static_cast<size_t>(total))) != VSG_OK) { vsg_seqset_destroy(s); return rc; }
+    VSG_CUDA_OK(cudaMemcpyAsync(tmp_ascii.p, cat, static_cast<size_t>(total), cudaMemcpyHostToDevice, c->stream));
+    d_ascii = static_cast<const char *>(tmp_ascii.p);
+  }
+  if (n > 0) {
+    VSG_CUDA_OK(cudaMemcpyAsync(s->b_off.p, h_off.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, c->stream));
+    VSG_CUDA_OK(cudaMemcpyAsync(s->b_len.p, s->h_len.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+  }
+  s->d.sym = static_cast<uint8_t *>(s->b_sym.p);
+  s->d.off = static_cast<int64_t *>(s->b_off.p);
+  s->d.len = static_cast<int32_t *>(s->b_len.p);
+  s->d.n = n;
+  s->h_nonacgt.assign(static_cast<size_t>(n), 0);
+  if (total > 0) {
+    int64_t const blocks = (total + 255) / 256;
+    encode_kernel<<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(d_ascii, static_cast<uint8_t *>(s->b_sym.p), total);
+    count_launch();
+  }
+  if (n > 0) {
+    DevBuf flag;
+    if ((rc = flag.reserve(static_cast<size_t>(n))) != VSG_OK) { vsg_seqset_destroy(s); return rc; }
+    int64_t const blocks = (n * 32 + 255) / 256;
+    nonacgt_kernel<<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(s->d, static_cast<uint8_t *>(flag.p));
+    count_launch();
+    VSG_CUDA_OK(cudaMemcpyAsync(s->h_nonacgt.data(), flag.p, static_cast<size_t>(n), cudaMemcpyDeviceToHost, c->stream));
+    VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+    flag.release();
+  } else {
+    VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+  }
+  tmp_ascii.release();
+  VSG_CUDA_OK(cudaGetLastError());
+  *out = s;
+  return VSG_OK;
+}
+
+extern "C" void vsg_seqset_destroy(vsg_seqset * s)
+{
+  if (s == nullptr) { return; }
+  cudaSetDevice(s->device);
+  s->b_sym.release(); s->b_off.release(); s->b_len.release();
+  delete s;
+}
+
+extern "C" int64_t vsg_seqset_count(const vsg_seqset * s) { return s != nullptr ? s->d.n : 0; }
+
+// ---- the aligner -----------------------------------------------------------------------------
+namespace {
+
+template <int R, bool G>
+void launch_fast_one(vsg_ctx * c, const DevSeqs & qs, const DevSeqs & ts, const FastTask * d_tasks, int n)
+{
+  int const blocks = (n + FAST_WARPS - 1) / FAST_WARPS;
+  nw_fast_kernel<R, G><<<blocks, FAST_WARPS * 32, 0, c->stream>>>(
+      c->sp, qs, ts, d_tasks, n, static_cast<uint8_t *>(c->dir.p), static_cast<uint2 *>(c->bnd.p),
+      static_cast<int32_t *>(c->stats.p));
+  count_launch();
+}
+
+void launch_fast(vsg_ctx * c, int R, bool general, const DevSeqs & qs, const DevSeqs & ts,
+                 const FastTask * d_tasks, int n)
+{
+  if (general) {
+    switch (R) {
+      case 4: launch_fast_one<4, true>(c, qs, ts, d_tasks, n); break;
+      case 8: launch_fast_one<8, true>(c, qs, ts, d_tasks, n); break;
+      default: launch_fast_one<16, true>(c, qs, ts, d_tasks, n); break;
+    }
+    return;
+  }
+  switch (R) {
+#define VSG_CASE(r) case r: launch_fast_one<r, false>(c, qs, ts, d_tasks, n); break;
+    VSG_CASE(1) VSG_CASE(2) VSG_CASE(3) VSG_CASE(4) VSG_CASE(5) VSG_CASE(6) VSG_CASE(7) VSG_CASE(8)
+    VSG_CASE(9) VSG_CASE(10) VSG_CASE(11) VSG_CASE(12) VSG_CASE(13) VSG_CASE(14) VSG_CASE(15)
+    default: launch_fast_one<16, false>(c, qs, ts, d_tasks, n); break;
+#undef VSG_CASE
+  }
+}
+
+struct HostPair {  // one aligned pair of the current chunk
+  PairDesc pd;
+};
+
+struct Chunk {
+  std::vector<FastTask> fast[2][FAST_RMAX + 1];  // [general][R]
+  std::vector<ExactTask> exact;
+  std::vector<PairDesc> pairs;
+  uint64_t dir_bytes = 0, bnd_elems = 0, he_elems = 0, cigar_bytes = 0;
+  int64_t cells = 0, nfast = 0, nexact = 0;
+  void clear()
+  {
+    for (auto & g : fast) { for (auto & v : g) { v.clear(); } }
+    exact.clear(); pairs.clear();
+    dir_bytes = bnd_elems = he_elems = cigar_bytes = 0;
+    cells = nfast = nexact = 0;
+  }
+  bool empty() const { return pairs.empty(); }
+};
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// enqueue forward + traceback (+ CIGAR packing) for one chunk and bring its results home
+int run_chunk(vsg_ctx * c, const vsg_seqset * qs, const vsg_seqset * ts, Chunk & ch, bool want_cigar,
+              int32_t * h_stats_all, std::vector<std::string> * cigars_out /* per pair slot */)
+{
+  int rc;
+  if ((rc = c->dir.reserve(ch.dir_bytes + 256)) != VSG_OK) { return rc; }
+  if ((rc = c->bnd.reserve(sizeof(uint2) * (ch.bnd_elems + 1))) != VSG_OK) { return rc; }
+  if ((rc = c->he.reserve(sizeof(int16_t) * (ch.he_elems + 1))) != VSG_OK) { return rc; }
+
+  // tasks: all fast classes back to back, then exact
+  size_t nfast_tasks = 0;
+  for (auto & g : ch.fast) { for (auto & v : g) { nfast_tasks += v.size(); } }
+  if ((rc = c->tasks_fast.reserve(sizeof(FastTask) * (nfast_tasks + 1))) != VSG_OK) { return rc; }
+  if ((rc = c->tasks_exact.reserve(sizeof(ExactTask) * (ch.exact.size() + 1))) != VSG_OK) { return rc; }
+  if ((rc = c->pairs.reserve(sizeof(PairDesc) * (ch.pairs.size() + 1))) != VSG_OK) { return rc; }
+  size_t const host_bytes = sizeof(FastTask) * nfast_tasks + sizeof(ExactTask) * ch.exact.size() +
+                            sizeof(PairDesc) * ch.pairs.size() + 64;
+  if ((rc = c->h_tasks.reserve(host_bytes)) != VSG_OK) { return rc; }
+  char * hp = static_cast<char *>(c->h_tasks.p);
+  FastTask * h_fast = reinterpret_cast<FastTask *>(hp);
+  size_t pos = 0;
+  for (auto & g : ch.fast) {
+    for (auto & v : g) {
+      // longest first: the tail of the grid is made of the short ones
+      std::sort(v.begin(), v.end(), [](const FastTask & a, const FastTask & b) { return a.dmax > b.dmax; });
+      if (!v.empty()) { std::memcpy(h_fast + pos, v.data(), sizeof(FastTask) * v.size()); }
+      pos += v.size();
+    }
+  }
+  ExactTask * h_exact = reinterpret_cast<ExactTask *>(hp + sizeof(FastTask) * nfast_tasks);
+  if (!ch.exact.empty()) { std::memcpy(h_exact, ch.exact.data(), sizeof(ExactTask) * ch.exact.size()); }
+  PairDesc * h_pairs = reinterpret_cast<PairDesc *>(hp + sizeof(FastTask) * nfast_tasks + sizeof(ExactTask) * ch.exact.size());
+  std::memcpy(h_pairs, ch.pairs.data(), sizeof(PairDesc) * ch.pairs.size());
+
+  if (nfast_tasks > 0) {
+    VSG_CUDA_OK(cudaMemcpyAsync(c->tasks_fast.p, h_fast, sizeof(FastTask) * nfast_tasks, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (!ch.exact.empty()) {
+    VSG_CUDA_OK(cudaMemcpyAsync(c->tasks_exact.p, h_exact, sizeof(ExactTask) * ch.exact.size(), cudaMemcpyHostToDevice, c->stream));
+  }
+  VSG_CUDA_OK(cudaMemcpyAsync(c->pairs.p, h_pairs, sizeof(PairDesc) * ch.pairs.size(), cudaMemcpyHostToDevice, c->stream));
+
+  VSG_CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
+  pos = 0;
+  for (int g = 0; g < 2; g++) {
+    for (int R = 1; R <= FAST_RMAX; R++) {
+      auto & v = ch.fast[g][R];
+      if (v.empty()) { continue; }
+      launch_fast(c, R, g != 0, qs->d, ts->d, static_cast<FastTask *>(c->tasks_fast.p) + pos, static_cast<int>(v.size()));
+      pos += v.size();
+    }
+  }
+  if (!ch.exact.empty()) {
+    int const n = static_cast<int>(ch.exact.size());
+    nw_exact_kernel<<<(n + 63) / 64, 64, 0, c->stream>>>(c->sp, qs->d, ts->d, static_cast<ExactTask *>(c->tasks_exact.p), n,
+                                                          static_cast<uint8_t *>(c->dir.p), static_cast<int16_t *>(c->he.p),
+                                                          static_cast<int32_t *>(c->stats.p));
+    count_launch();
+  }
+  VSG_CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
+
+  int const np = static_cast<int>(ch.pairs.size());
+  if (want_cigar) {
+    if ((rc = c->cigar_scratch.reserve(ch.cigar_bytes + 64)) != VSG_OK) { return rc; }
+    traceback_kernel<true><<<(np + 127) / 128, 128, 0, c->stream>>>(
+        c->sp, qs->d, ts->d, static_cast<PairDesc *>(c->pairs.p), np, static_cast<uint8_t *>(c->dir.p),
+        static_cast<char *>(c->cigar_scratch.p), static_cast<int32_t *>(c->stats.p));
+  } else {
+    traceback_kernel<false><<<(np + 127) / 128, 128, 0, c->stream>>>(
+        c->sp, qs->d, ts->d, static_cast<PairDesc *>(c->pairs.p), np, static_cast<uint8_t *>(c->dir.p),
+        nullptr, static_cast<int32_t *>(c->stats.p));
+  }
+  count_launch();
+  VSG_CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
+
+  std::vector<int64_t> h_offs;
+  if (want_cigar) {
+    if ((rc = c->cigar_len.reserve(sizeof(int64_t) * (np + 1))) != VSG_OK) { return rc; }
+    if ((rc = c->cigar_offs.reserve(sizeof(int64_t) * (np + 1))) != VSG_OK) { return rc; }
+    cigar_len_kernel<<<(np + 255) / 256, 256, 0, c->stream>>>(static_cast<PairDesc *>(c->pairs.p),
+                                                               static_cast<int32_t *>(c->stats.p), np,
+                                                               static_cast<int64_t *>(c->cigar_len.p));
+    count_launch();
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, static_cast<int64_t *>(c->cigar_len.p),
+                                  static_cast<int64_t *>(c->cigar_offs.p), np, c->stream);
+    if ((rc = c->cub_tmp.reserve(tmp_bytes + 16)) != VSG_OK) { return rc; }
+    cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, static_cast<int64_t *>(c->cigar_len.p),
+                                  static_cast<int64_t *>(c->cigar_offs.p), np, c->stream);
+    count_launch();
+    // dense size <= scratch size
+    if ((rc = c->cigar_dense.reserve(ch.cigar_bytes + 64)) != VSG_OK) { return rc; }
+    cigar_gather_kernel<<<np, 64, 0, c->stream>>>(static_cast<PairDesc *>(c->pairs.p), np, qs->d, ts->d,
+                                                   static_cast<int32_t *>(c->stats.p),
+                                                   static_cast<int64_t *>(c->cigar_offs.p),
+                                                   static_cast<char *>(c->cigar_scratch.p),
+                                                   static_cast<char *>(c->cigar_dense.p));
+    count_launch();
+    h_offs.resize(static_cast<size_t>(np));
+    VSG_CUDA_OK(cudaMemcpyAsync(h_offs.data(), c->cigar_offs.p, sizeof(int64_t) * np, cudaMemcpyDeviceToHost, c->stream));
+  }
+  VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+  VSG_CUDA_OK(cudaGetLastError());
+
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->prof_fwd_ms += ms;
+  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->prof_tb_ms += ms;
+  c->prof_cells += ch.cells; c->prof_fast += ch.nfast; c->prof_exact += ch.nexact;
+
+  // stats of this chunk's pairs: they are scattered over the slot array; copy the covering range
+  int lo = INT32_MAX, hi = -1;
+  for (auto const & pd : ch.pairs) { lo = std::min(lo, pd.out); hi = std::max(hi, pd.out); }
+  if (hi >= lo) {
+    size_t const words = static_cast<size_t>(hi - lo + 1) * VSG_STAT_WORDS;
+    if ((rc = c->h_stats.reserve(words * sizeof(int32_t))) != VSG_OK) { return rc; }
+    VSG_CUDA_OK(cudaMemcpyAsync(c->h_stats.p, static_cast<int32_t *>(c->stats.p) + static_cast<size_t>(lo) * VSG_STAT_WORDS,
+                                words * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<char> dense;
+    if (want_cigar) {
+      // total text bytes = offs[np-1] + len[np-1]; fetch the whole used prefix
+      VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+    VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+    int32_t const * hs = static_cast<int32_t *>(c->h_stats.p);
+    for (auto const & pd : ch.pairs) {
+      std::memcpy(h_stats_all + static_cast<size_t>(pd.out) * VSG_STAT_WORDS,
+                  hs + static_cast<size_t>(pd.out - lo) * VSG_STAT_WORDS, sizeof(int32_t) * VSG_STAT_WORDS);
+    }
+    if (want_cigar) {
+      int64_t total = 0;
+      for (int p = 0; p < np; p++) {
+        total = std::max<int64_t>(total, h_offs[p] + h_stats_all[static_cast<size_t>(ch.pairs[p].out) * VSG_STAT_WORDS + VSG_STAT_CIGARLEN] + 1);
+      }
+      dense.resize(static_cast<size_t>(total) + 1);
+      VSG_CUDA_OK(cudaMemcpyAsync(dense.data(), c->cigar_dense.p, static_cast<size_t>(total), cudaMemcpyDeviceToHost, c->stream));
+      VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+      for (int p = 0; p < np; p++) {
+        (*cigars_out)[static_cast<size_t>(ch.pairs[p].out)] = std::string(dense.data() + h_offs[p]);
+      }
+    }
+  }
+  return VSG_OK;
+}
+
+}  // namespace
+
+extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vsg_seqset * targets,
+                               int64_t npairs, const uint32_t * qidx, const uint32_t * tidx,
+                               int16_t * score, uint16_t * aligned, uint16_t * matches,
+                               uint16_t * mismatches, uint16_t * gaps, int32_t * trims,
+                               char * cigar_buf, int64_t cigar_cap, int64_t * cigar_off)
+{
+  if (c == nullptr || queries == nullptr || targets == nullptr || npairs < 0 ||
+      (npairs > 0 && (qidx == nullptr || tidx == nullptr || score == nullptr))) {
+    Error::set("vsg_align_pairs: bad argument");
+    return VSG_EINVAL;
+  }
+  if (npairs > (1LL << 30)) { Error::set("vsg_align_pairs: too many pairs in one call"); return VSG_EINVAL; }
+  VSG_CUDA_OK(cudaSetDevice(c->device));
+  bool const want_cigar = (cigar_buf != nullptr);
+  if (want_cigar && cigar_off == nullptr) { Error::set("vsg_align_pairs: cigar_off required with cigar_buf"); return VSG_EINVAL; }
+  c->prof_cells = c->prof_fast = c->prof_exact = 0;
+  c->prof_fwd_ms = c->prof_tb_ms = 0.f;
+
+  std::vector<int32_t> st(static_cast<size_t>(npairs) * VSG_STAT_WORDS, 0);
+  std::vector<std::string> cigars;
+  if (want_cigar) { cigars.resize(static_cast<size_t>(npairs)); }
+  int rc;
+  if ((rc = c->stats.reserve(sizeof(int32_t) * VSG_STAT_WORDS * static_cast<size_t>(npairs) + 64)) != VSG_OK) { return rc; }
+
+  ScoreParams const & sp = c->sp;
+  Chunk ch;
+  struct Cand { int64_t slot; uint32_t t; int32_t d; bool general; };
+  std::vector<Cand> group_fast;
+
+  auto sentinel = [&](int64_t i) {
+    int32_t * s = &st[static_cast<size_t>(i) * VSG_STAT_WORDS];
+    std::memset(s, 0, sizeof(int32_t) * VSG_STAT_WORDS);
+    s[VSG_STAT_SCORE] = VSG_SCORE_SENTINEL;
+  };
+
+  auto flush_chunk = [&]() -> int {
+    if (ch.empty()) { return VSG_OK; }
+    int const r = run_chunk(c, queries, targets, ch, want_cigar, st.data(), want_cigar ? &cigars : nullptr);
+    ch.clear();
+    return r;
+  };
+
+  auto add_pairdesc = [&](uint32_t q, uint32_t t, int kind, int64_t slot, int R, int half, int dmax, uint64_t dir_off) {
+    PairDesc pd{};
+    pd.q = q; pd.t = t; pd.dir_off = dir_off; pd.kind = kind; pd.out = static_cast<int32_t>(slot);
+    pd.R = R; pd.half = half; pd.dmax = dmax;
+    pd.cigar_off = ch.cigar_bytes;
+    ch.cigar_bytes += static_cast<uint64_t>(queries->h_len[q]) + static_cast<uint64_t>(targets->h_len[t]) + 2;
+    ch.pairs.push_back(pd);
+  };
+
+  int64_t i = 0;
+  while (i < npairs) {
+    uint32_t const q = qidx[i];
+    if (q >= static_cast<uint64_t>(queries->d.n)) { Error::set("vsg_align_pairs: query index out of range"); return VSG_EINVAL; }
+    int64_t j = i;
+    while (j < npairs && qidx[j] == q) { j++; }
+    int const Q = queries->h_len[q];
+    bool const q_general = queries->h_nonacgt[q] != 0;
+    group_fast.clear();
+    for (int64_t k = i; k < j; k++) {
+      uint32_t const t = tidx[k];
+      if (t >= static_cast<uint64_t>(targets->d.n)) { Error::set("vsg_align_pairs: target index out of range"); return VSG_EINVAL; }
+      int const D = targets->h_len[t];
+      if (sp.fallback) { sentinel(k); continue; }  // align_simd.cpp:1463-1479
+      if (Q == 0) {                                // align_simd.cpp:1481-1539
+        int32_t * s = &st[static_cast<size_t>(k) * VSG_STAT_WORDS];
+        std::memset(s, 0, sizeof(int32_t) * VSG_STAT_WORDS);
+        if (!fits16(0, D)) { s[VSG_STAT_SCORE] = VSG_SCORE_SENTINEL; continue; }
+        s[VSG_STAT_ALIGNED] = D; s[VSG_STAT_GAPS] = D;
+        if (D > 0) {
+          int64_t const a = -static_cast<int64_t>(sp.go[T_L]) - static_cast<int64_t>(D) * sp.ge[T_L];
+          int64_t const b = -static_cast<int64_t>(sp.go[T_R]) - static_cast<int64_t>(D) * sp.ge[T_R];
+          s[VSG_STAT_SCORE] = static_cast<int16_t>(std::max(a, b));
+          s[VSG_STAT_TRIM_LEFT] = -D; s[VSG_STAT_TRIM_RIGHT] = -D;
+          if (want_cigar) { cigars[static_cast<size_t>(k)] = std::to_string(D) + "I"; }
+          s[VSG_STAT_CIGARLEN] = static_cast<int32_t>(std::to_string(D).size() + 1);
+        }
+        continue;
+      }
+      if (D == 0 || !fits16(Q, D)) { sentinel(k); continue; }  // align_simd.cpp:1867-1882
+      bool const general = q_general || targets->h_nonacgt[t] != 0;
+      int R, ns;
+      fast_shape(Q, general, R, ns);
+      if (!c->fast_disabled && fast_path_ok(sp, ns * 32 * R, D)) {
+        group_fast.push_back(Cand{k, t, D, general});
+      } else {
+        uint64_t const dirb = align_up(static_cast<uint64_t>(Q) * D, 16);
+        if (!ch.empty() && ch.dir_bytes + dirb > c->dir_budget) { if ((rc = flush_chunk()) != VSG_OK) { return rc; } }
+        ExactTask et{};
+        et.q = q; et.t = t; et.out = static_cast<int32_t>(k);
+        et.dir_off = ch.dir_bytes; et.he_off = ch.he_elems;
+        add_pairdesc(q, t, 1, k, 0, 0, 0, ch.dir_bytes);
+        ch.dir_bytes += dirb;
+        ch.he_elems += 2ULL * Q;
+        ch.exact.push_back(et);
+        ch.cells += static_cast<int64_t>(Q) * D; ch.nexact++;
+      }
+    }
+    // pair the fast candidates two by two, similar lengths together
+    if (!group_fast.empty()) {
+      std::sort(group_fast.begin(), group_fast.end(), [](const Cand & a, const Cand & b) {
+        if (a.general != b.general) { return a.general < b.general; }
+        if (a.d != b.d) { return a.d > b.d; }
+        return a.slot < b.slot;
+      });
+      size_t k = 0;
+      while (k < group_fast.size()) {
+        Cand const & a = group_fast[k];
+        bool const pair2 = (k + 1 < group_fast.size()) && (group_fast[k + 1].general == a.general);
+        Cand const & b = pair2 ? group_fast[k + 1] : a;
+        int R, ns;
+        fast_shape(Q, a.general, R, ns);
+        int const dmax = std::max(a.d, b.d);
+        uint64_t const dirb = static_cast<uint64_t>(ns) * (dmax + 31) * 32 * fast_rw(R) * 4;
+        if (!ch.empty() && ch.dir_bytes + dirb > c->dir_budget) { if ((rc = flush_chunk()) != VSG_OK) { return rc; } }
+        FastTask ft{};
+        ft.q = q; ft.tlo = a.t; ft.thi = b.t;
+        ft.out_lo = static_cast<int32_t>(a.slot);
+        ft.out_hi = pair2 ? static_cast<int32_t>(b.slot) : -1;
+        ft.dmax = dmax;
+        ft.dir_off = ch.dir_bytes;
+        ft.bnd_off = ch.bnd_elems;
+        add_pairdesc(q, a.t, 0, a.slot, R, 0, dmax, ch.dir_bytes);
+        if (pair2) { add_pairdesc(q, b.t, 0, b.slot, R, 1, dmax, ch.dir_bytes); }
+        ch.dir_bytes += dirb;
+        if (ns > 1) { ch.bnd_elems += static_cast<uint64_t>(dmax); }
+        ch.fast[a.general ? 1 : 0][R].push_back(ft);
+        ch.cells += static_cast<int64_t>(Q) * a.d + (pair2 ? static_cast<int64_t>(Q) * b.d : 0);
+        ch.nfast += pair2 ? 2 : 1;
+        k += pair2 ? 2 : 1;
+      }
+    }
+    i = j;
+  }
+  if ((rc = flush_chunk()) != VSG_OK) { return rc; }
+
+  int64_t cpos = 0;
+  for (int64_t k = 0; k < npairs; k++) {
+    int32_t const * s = &st[static_cast<size_t>(k) * VSG_STAT_WORDS];
+    score[k] = static_cast<int16_t>(s[VSG_STAT_SCORE]);
+    if (aligned != nullptr) { aligned[k] = static_cast<uint16_t>(s[VSG_STAT_ALIGNED]); }
+    if (matches != nullptr) { matches[k] = static_cast<uint16_t>(s[VSG_STAT_MATCHES]); }
+    if (mismatches != nullptr) { mismatches[k] = static_cast<uint16_t>(s[VSG_STAT_MISMATCHES]); }
+    if (gaps != nullptr) { gaps[k] = static_cast<uint16_t>(s[VSG_STAT_GAPS]); }
+    if (trims != nullptr) {
+      int const tl = s[VSG_STAT_TRIM_LEFT], tr = s[VSG_STAT_TRIM_RIGHT];
+      trims[4 * k + 0] = tl > 0 ? tl : 0;   // leading D  -> trim_q_left
+      trims[4 * k + 1] = tl < 0 ? -tl : 0;  // leading I  -> trim_t_left
+      trims[4 * k + 2] = tr > 0 ? tr : 0;
+      trims[4 * k + 3] = tr < 0 ? -tr : 0;
+    }
+    if (want_cigar) {
+      std::string const & cg = cigars[static_cast<size_t>(k)];
+      if (cpos + static_cast<int64_t>(cg.size()) + 1 > cigar_cap) { Error::set("vsg_align_pairs: cigar buffer too small"); return VSG_ECAP; }
+      cigar_off[k] = cpos;
+      std::memcpy(cigar_buf + cpos, cg.c_str(), cg.size() + 1);
+      cpos += static_cast<int64_t>(cg.size()) + 1;
+    }
+  }
+  if (want_cigar) { cigar_off[npairs] = cpos; }
+  return VSG_OK;
+}
+
+extern "C" int vsg_last_align_profile(vsg_ctx * c, int64_t * cells, float * fwd_ms, float * traceback_ms,
+                                      int64_t * fast_pairs, int64_t * exact_pairs)
+{
+  if (c == nullptr) { return VSG_EINVAL; }
+  if (cells != nullptr) { *cells = c->prof_cells; }
+  if (fwd_ms != nullptr) { *fwd_ms = c->prof_fwd_ms; }
+  if (traceback_ms != nullptr) { *traceback_ms = c->prof_tb_ms; }
+  if (fast_pairs != nullptr) { *fast_pairs = c->prof_fast; }
+  if (exact_pairs != nullptr) { *exact_pairs = c->prof_exact; }
+  return VSG_OK;
+}

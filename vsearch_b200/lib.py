@@ -1,0 +1,228 @@
+"""ctypes loader for the product library ``vsearch_b200/csrc/libvsg.so`` (C ABI: include/vsg.h).
+
+This is host-side plumbing for tests and bench.py only.  There is no CPU implementation behind it:
+if the library or a CUDA device is missing every call fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(ROOT, "vsearch_b200", "csrc", "libvsg.so")
+HEADER = os.path.join(ROOT, "include", "vsg.h")
+
+DEFAULT_PEN = (2, -4, 1, 1, 18, 18, 1, 1, 1, 1, 2, 2, 1, 1)
+STAT_WORDS = 8
+
+_lib = None
+
+
+class VsgError(RuntimeError):
+    pass
+
+
+class Scoring(C.Structure):
+    _fields_ = [("v", C.c_int64 * 14), ("n_mismatch", C.c_int32)]
+
+
+class SearchOpts(C.Structure):
+    _fields_ = [("id", C.c_double), ("weak_id", C.c_double), ("maxaccepts", C.c_int32),
+                ("maxrejects", C.c_int32), ("wordlength", C.c_int32), ("minwordmatches", C.c_int32),
+                ("iddef", C.c_int32), ("strand_both", C.c_int32), ("mask_lower", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class SearchResult(C.Structure):
+    _fields_ = [("target", C.c_int32), ("matches", C.c_int32), ("mismatches", C.c_int32),
+                ("gaps", C.c_int32), ("alignment_length", C.c_int32), ("query_length", C.c_int32),
+                ("target_length", C.c_int32), ("accepted", C.c_int32), ("strand", C.c_int32),
+                ("nwscore", C.c_int32), ("id", C.c_double)]
+
+
+def declared_symbols() -> List[str]:
+    """Every function name include/vsg.h declares."""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vsg_[a-z0-9_]+)\s*\(", text)))
+
+
+def load():
+    """dlopen libvsg.so and check that it exports everything the header declares."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VsgError(f"{LIB_PATH} not built: run `python __graft_entry__.py` (nvcc, sm_100a). "
+                       "There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    if missing:
+        raise VsgError(f"libvsg.so does not export: {missing}")
+    lib.vsg_last_error.restype = C.c_char_p
+    lib.vsg_version.restype = C.c_char_p
+    lib.vsg_launch_count.restype = C.c_int64
+    lib.vsg_ctx_stream.restype = C.c_void_p
+    lib.vsg_seqset_count.restype = C.c_int64
+    _lib = lib
+    return lib
+
+
+def launch_count() -> int:
+    return int(load().vsg_launch_count())
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise VsgError(f"{what} failed ({rc}): {load().vsg_last_error().decode()}")
+
+
+def _ptr(a: Optional[np.ndarray], t):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+@dataclass
+class AlignResult:
+    score: np.ndarray
+    aligned: np.ndarray
+    matches: np.ndarray
+    mismatches: np.ndarray
+    gaps: np.ndarray
+    trims: np.ndarray
+    cigars: Optional[List[str]]
+    cells: int = 0
+    fwd_ms: float = 0.0
+    tb_ms: float = 0.0
+    fast_pairs: int = 0
+    exact_pairs: int = 0
+
+
+class SeqSetHandle:
+    def __init__(self, ctx: "Context", h, n: int, lens: np.ndarray):
+        self.ctx, self.h, self.n, self.lens = ctx, h, n, lens
+
+    def close(self):
+        if self.h:
+            load().vsg_seqset_destroy(self.h)
+            self.h = None
+
+
+class IndexHandle:
+    def __init__(self, h):
+        self.h = h
+
+    def close(self):
+        if self.h:
+            load().vsg_index_destroy(self.h)
+            self.h = None
+
+
+class Context:
+    """vsg_ctx: one CUDA stream + scratch; mirrors the reference's per-thread s16info_s."""
+
+    def __init__(self, device: int = 0, pen=DEFAULT_PEN, n_mismatch: int = 0):
+        lib = load()
+        sc = Scoring()
+        for i in range(14):
+            sc.v[i] = int(pen[i])
+        sc.n_mismatch = int(n_mismatch)
+        self.h = C.c_void_p()
+        _check(lib.vsg_ctx_create(C.c_int(device), C.byref(sc), C.byref(self.h)), "vsg_ctx_create")
+
+    def close(self):
+        if self.h:
+            load().vsg_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        _check(load().vsg_ctx_sync(self.h), "vsg_ctx_sync")
+
+    def seqset(self, ss) -> SeqSetHandle:
+        """Upload a synth.SeqSet-like object (cat uint8, offs int64, lens int32) into HBM."""
+        h = C.c_void_p()
+        cat = np.ascontiguousarray(ss.cat, dtype=np.uint8)
+        offs = np.ascontiguousarray(ss.offs, dtype=np.int64)
+        lens = np.ascontiguousarray(ss.lens, dtype=np.int32)
+        _check(load().vsg_seqset_create(self.h, _ptr(cat, C.c_char), _ptr(offs, C.c_int64),
+                                        _ptr(lens, C.c_int32), C.c_int64(lens.shape[0]), C.c_int(1),
+                                        C.byref(h)), "vsg_seqset_create")
+        return SeqSetHandle(self, h, int(lens.shape[0]), lens)
+
+    def seqset_from_device(self, d_cat: int, d_off: int, d_len: int, n: int) -> SeqSetHandle:
+        """Adopt ASCII/offset/length arrays that already live in this device's HBM (raw pointers)."""
+        h = C.c_void_p()
+        _check(load().vsg_seqset_create(self.h, C.cast(C.c_void_p(d_cat), C.POINTER(C.c_char)),
+                                        C.cast(C.c_void_p(d_off), C.POINTER(C.c_int64)),
+                                        C.cast(C.c_void_p(d_len), C.POINTER(C.c_int32)),
+                                        C.c_int64(n), C.c_int(0), C.byref(h)), "vsg_seqset_create")
+        return SeqSetHandle(self, h, n, None)
+
+    def align_pairs(self, qs: SeqSetHandle, ts: SeqSetHandle, qidx: np.ndarray, tidx: np.ndarray,
+                    cigar: bool = False) -> AlignResult:
+        lib = load()
+        qidx = np.ascontiguousarray(qidx, dtype=np.uint32)
+        tidx = np.ascontiguousarray(tidx, dtype=np.uint32)
+        n = int(qidx.shape[0])
+        score = np.zeros(n, dtype=np.int16)
+        al = np.zeros(n, dtype=np.uint16); ma = np.zeros(n, dtype=np.uint16)
+        mi = np.zeros(n, dtype=np.uint16); ga = np.zeros(n, dtype=np.uint16)
+        trims = np.zeros((n, 4), dtype=np.int32)
+        cbuf = coff = None
+        cap = 0
+        if cigar:
+            cap = int((qs.lens[qidx].astype(np.int64) + ts.lens[tidx].astype(np.int64) + 2).sum()) + 16
+            cbuf = np.zeros(cap, dtype=np.uint8)
+            coff = np.zeros(n + 1, dtype=np.int64)
+        _check(lib.vsg_align_pairs(self.h, qs.h, ts.h, C.c_int64(n), _ptr(qidx, C.c_uint32),
+                                   _ptr(tidx, C.c_uint32), _ptr(score, C.c_int16), _ptr(al, C.c_uint16),
+                                   _ptr(ma, C.c_uint16), _ptr(mi, C.c_uint16), _ptr(ga, C.c_uint16),
+                                   _ptr(trims, C.c_int32), _ptr(cbuf, C.c_char), C.c_int64(cap),
+                                   _ptr(coff, C.c_int64)), "vsg_align_pairs")
+        cigs = None
+        if cigar:
+            raw = cbuf.tobytes()
+            cigs = [raw[int(coff[i]):int(coff[i + 1]) - 1].decode() for i in range(n)]
+        cells = C.c_int64(); f = C.c_float(); t = C.c_float(); fp = C.c_int64(); ep = C.c_int64()
+        lib.vsg_last_align_profile(self.h, C.byref(cells), C.byref(f), C.byref(t), C.byref(fp), C.byref(ep))
+        return AlignResult(score, al, ma, mi, ga, trims, cigs, cells.value, f.value, t.value,
+                           fp.value, ep.value)
+
+    def index(self, db: SeqSetHandle, wordlength: int = 8, mask_lower: int = 0) -> IndexHandle:
+        h = C.c_void_p()
+        _check(load().vsg_index_create(self.h, db.h, C.c_int(wordlength), C.c_int(mask_lower),
+                                       C.byref(h)), "vsg_index_create")
+        return IndexHandle(h)
+
+    def rank(self, ix: IndexHandle, qs: SeqSetHandle, q0: int, nq: int, minwordmatches: int,
+             tophits: int, mask_lower: int = 0):
+        seqno = np.zeros((nq, tophits), dtype=np.uint32)
+        count = np.zeros((nq, tophits), dtype=np.uint32)
+        nc = np.zeros(nq, dtype=np.int32)
+        _check(load().vsg_rank(self.h, ix.h, qs.h, C.c_int64(q0), C.c_int64(nq), C.c_int(minwordmatches),
+                               C.c_int(tophits), C.c_int(mask_lower), _ptr(seqno, C.c_uint32),
+                               _ptr(count, C.c_uint32), _ptr(nc, C.c_int32)), "vsg_rank")
+        return seqno, count, nc
+
+    def search(self, ix: IndexHandle, db: SeqSetHandle, qs: SeqSetHandle, q0: int, nq: int,
+               opts: SearchOpts, max_results: int):
+        res = (SearchResult * (nq * max_results))()
+        counts = np.zeros(nq, dtype=np.int32)
+        work = np.zeros(2, dtype=np.int64)
+        _check(load().vsg_search_batch(self.h, ix.h, db.h, qs.h, C.c_int64(q0), C.c_int64(nq),
+                                       C.byref(opts), res, C.c_int(max_results), _ptr(counts, C.c_int32),
+                                       _ptr(work, C.c_int64)), "vsg_search_batch")
+        return res, counts, work
+
+
+def default_search_opts() -> SearchOpts:
+    o = SearchOpts()
+    load().vsg_search_opts_default(C.byref(o))
+    return o
