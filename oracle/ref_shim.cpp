@@ -106,6 +106,15 @@ int vsref_unique_count(int wordlength, const char * seq, int len, int mask_lower
   return static_cast<int>(n);
 }
 
+/* DUST soft-masking of one sequence in place (core/mask.cpp:79-188 via dust()); used to
+   generate pre-masked golden fixtures: the product takes soft-masked input as given. */
+void vsref_dust(char * seq, int len)
+{
+  Parameters p;
+  p.opt_hardmask = false;
+  dust(seq, len, p);
+}
+
 /* Build a reference Database + Dbindex from plain buffers and open a library session.
    Only one may exist at a time (the reference serialises sessions, vsearch.cc:283). */
 void * vsref_db_create(int n, const char * cat, const int64_t * off, const int * len,

@@ -553,6 +553,28 @@ __global__ void encode_kernel(const char * __restrict__ ascii, uint8_t * __restr
   }
 }
 
+// reverse complement of sequences [q0, q0+n) of `src` into a compact set (reference
+// utils/reverse_complement.cpp:71-84 + chrmap_complement, utils/maps.cpp:121-151): the complement
+// of a 4-bit IUPAC code is its bit reversal; non-IUPAC bytes become 'N' (upper case); case is kept.
+__global__ void revcomp_kernel(DevSeqs src, int64_t q0, int64_t n, const int64_t * __restrict__ dst_off,
+                               uint8_t * __restrict__ dst)
+{
+  int64_t const w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  int const lane = threadIdx.x & 31;
+  if (w >= n) { return; }
+  uint8_t const * p = src.sym + src.off[q0 + w];
+  int const len = src.len[q0 + w];
+  uint8_t * o = dst + dst_off[w];
+  for (int i = lane; i < len; i += 32) {
+    int const s = p[len - 1 - i];
+    int const c = s & 15;
+    int r;
+    if (c == 0) { r = 15; }
+    else { r = ((c & 1) << 3) | ((c & 2) << 1) | ((c & 4) >> 1) | ((c & 8) >> 3); r |= (s & 16); }
+    o[i] = static_cast<uint8_t>(r);
+  }
+}
+
 __global__ void nonacgt_kernel(DevSeqs s, uint8_t * __restrict__ flag)
 {
   int64_t const w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;

@@ -1,10 +1,415 @@
-// rank.cu — placeholder until the ranker kernels land (next commit): fails loudly.
+// rank.cu — k-mer index in HBM and the candidate ranker (sm_100a).
+//
+// Replaces, for whole batches of queries at once,
+//   unique_count            (reference core/unique.cpp:155-353)   distinct unmasked k-mers of a sequence
+//   Dbindex::prepare/add_*  (core/dbindex.cpp:121-255)            k-mer -> targets postings
+//   search_topscores        (core/searchcore.cpp:260-340)         per-target shared-k-mer counts,
+//                                                                 threshold, best `tophits` targets
+//   minheap_*               (core/minheap.cpp:82-263)             order: count desc, length asc, seqno asc
+//
+// Layout.  The database is cut into SHARDS of at most 32768 consecutive targets.  A shard stores
+// CSR postings: start[4^k + 1] (u32) and post[] holding 15-bit shard-local target numbers as u16
+// (half the bytes of the reference's u32 lists; the reference's per-k-mer bitmaps for very frequent
+// k-mers, dbindex.cpp:212-229, are a storage variant with the same meaning and are not needed).
+// One CTA ranks one query: for every shard it zeroes 32768 16-bit counters in SHARED memory,
+// streams the postings of the query's distinct k-mers (coalesced u16 loads, one warp per list)
+// into them with shared-memory atomics, scans the counters against the threshold and appends the
+// survivors as 64-bit sort keys to a candidate list that is bitonic-sorted and cut to `tophits`
+// whenever it fills up and once at the end.  HBM traffic per query is the postings themselves
+// (2 B each) — the counters never leave the SM.
 #include "vsg_internal.h"
+
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstring>
+
+namespace vsg {
+
+constexpr int SHARD_BITS = 15;
+constexpr int SHARD = 1 << SHARD_BITS;  // targets per shard
+constexpr int RANK_THREADS = 256;
+constexpr int KMER_CAP = 2048;          // distinct-k-mer capacity per query (query length <= 2047 + k)
+constexpr int CAND_CAP = 2048;          // candidate keys held in shared memory
+constexpr int TOPHITS_MAX = 1024;
+constexpr int SCAN_SEG_WORDS = 512;     // counters are scanned 1024 at a time (<= 1024 new candidates)
+
+struct ShardDev {
+  const uint32_t * start;  // 4^k + 1
+  const uint16_t * post;
+  int32_t t0;              // first target of the shard
+  int32_t nt;              // targets in the shard
+};
+
+__device__ __forceinline__ bool sym_bad(int s, int mask_lower)
+{
+  int const c = s & 15;
+  bool const single = (c == 1) | (c == 2) | (c == 4) | (c == 8);
+  return !single || (mask_lower && (s & 16));
+}
+__device__ __forceinline__ uint32_t sym_2bit(int s)
+{
+  int const c = s & 15;
+  return (c == 2) ? 1u : (c == 4) ? 2u : (c == 8) ? 3u : 0u;
+}
+
+// k-mer ending at position p (p >= k-1); returns false when the window holds a masked symbol
+__device__ __forceinline__ bool kmer_at(const uint8_t * __restrict__ s, int p, int k, int mask_lower,
+                                        uint32_t & out)
+{
+  uint32_t v = 0;
+  bool bad = false;
+  for (int j = p - k + 1; j <= p; j++) {
+    int const c = s[j];
+    bad |= sym_bad(c, mask_lower);
+    v = (v << 2) | sym_2bit(c);
+  }
+  out = v;
+  return !bad;
+}
+
+// ---- index build: pass 1 counts, pass 2 fills; one CTA per target, shared-memory bitmap dedupe ----
+template <bool FILL>
+__global__ void index_build_kernel(DevSeqs db, int t0, int nt, int k, int mask_lower,
+                                   uint32_t * __restrict__ count /* pass1: counts; pass2: fill cursors */,
+                                   const uint32_t * __restrict__ start, uint16_t * __restrict__ post)
+{
+  extern __shared__ uint32_t bitmap[];
+  int const lt = blockIdx.x;
+  if (lt >= nt) { return; }
+  int const words = (1 << (2 * k)) >> 5;
+  for (int i = threadIdx.x; i < (words > 0 ? words : 1); i += blockDim.x) { bitmap[i] = 0; }
+  __syncthreads();
+  int64_t const t = static_cast<int64_t>(t0) + lt;
+  const uint8_t * __restrict__ s = db.sym + db.off[t];
+  int const len = db.len[t];
+  for (int p = k - 1 + threadIdx.x; p < len; p += blockDim.x) {
+    uint32_t km;
+    if (kmer_at(s, p, k, mask_lower, km)) {
+      uint32_t const bit = 1u << (km & 31);
+      uint32_t const old = atomicOr(&bitmap[km >> 5], bit);
+      if ((old & bit) == 0) {  // first occurrence in this target
+        if (FILL) {
+          uint32_t const pos = atomicAdd(&count[km], 1u);
+          post[static_cast<size_t>(start[km]) + pos] = static_cast<uint16_t>(lt);
+        } else {
+          atomicAdd(&count[km], 1u);
+        }
+      }
+    }
+  }
+}
+
+// ---- bitonic sort helpers on shared memory (descending for keys, ascending for k-mers) ----------
+template <typename T, bool DESC>
+__device__ void bitonic_sort_shared(T * a, int n /* power of two */)
+{
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
+        int const lo = 2 * i - (i & (stride - 1));
+        int const hi = lo + stride;
+        bool const up = ((lo & size) == 0);
+        T const x = a[lo], y = a[hi];
+        bool const sw = DESC ? (up ? (x < y) : (x > y)) : (up ? (x > y) : (x < y));
+        if (sw) { a[lo] = y; a[hi] = x; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int next_pow2(int v)
+{
+  int p = 1;
+  while (p < v) { p <<= 1; }
+  return p;
+}
+
+// key: larger = better.  count (15 bits) | ~length (25 bits) | ~seqno (24 bits)
+__device__ __forceinline__ uint64_t make_key(uint32_t count, uint32_t len, uint32_t seqno)
+{
+  uint32_t const l = len > 0x1ffffffu ? 0x1ffffffu : len;
+  return (static_cast<uint64_t>(count) << 49) | (static_cast<uint64_t>(0x1ffffffu - l) << 24) |
+         static_cast<uint64_t>(0xffffffu - seqno);
+}
+
+__global__ void __launch_bounds__(RANK_THREADS)
+rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restrict__ shards, int nshards,
+            int k, int mask_lower, int minwordmatches, int tophits,
+            uint32_t * __restrict__ out_seqno, uint32_t * __restrict__ out_count, int32_t * __restrict__ out_n,
+            int32_t * __restrict__ status)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint32_t * const counters = reinterpret_cast<uint32_t *>(smem);                 // SHARD/2 words
+  uint64_t * const cand = reinterpret_cast<uint64_t *>(smem + SHARD * 2);         // CAND_CAP
+  uint32_t * const kmers = reinterpret_cast<uint32_t *>(smem + SHARD * 2 + CAND_CAP * 8);  // KMER_CAP
+  uint32_t * const lbeg = kmers + KMER_CAP;                                       // KMER_CAP
+  uint32_t * const llen = lbeg + KMER_CAP;                                        // KMER_CAP
+  __shared__ int s_ncand, s_nk;
+
+  int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NWARPS = RANK_THREADS / 32;
+
+  for (int qi = blockIdx.x; qi < nq; qi += gridDim.x) {
+    int64_t const q = q0 + qi;
+    const uint8_t * __restrict__ s = qs.sym + qs.off[q];
+    int const len = qs.len[q];
+    int const nwin = len - k + 1;
+    if (threadIdx.x == 0) { s_ncand = 0; s_nk = 0; }
+    if (nwin > KMER_CAP) {
+      if (threadIdx.x == 0) { out_n[qi] = 0; atomicExch(status, 1); }
+      continue;
+    }
+    // 1. the query's k-mers, sorted, duplicates and masked windows invalidated (0xffffffff)
+    int const np2 = next_pow2(nwin > 1 ? nwin : 1);
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+      uint32_t km = 0xffffffffu;
+      if (i < nwin) {
+        uint32_t v;
+        if (kmer_at(s, i + k - 1, k, mask_lower, v)) { km = v; }
+      }
+      kmers[i] = km;
+    }
+    bitonic_sort_shared<uint32_t, false>(kmers, np2);
+    int mine = 0;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+      uint32_t const v = kmers[i];
+      bool const keep = (v != 0xffffffffu) && (i == 0 || kmers[i - 1] != v);
+      lbeg[i] = keep ? 1u : 0u;  // temporary keep flag
+      mine += keep;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) { if (lbeg[i] == 0u) { kmers[i] = 0xffffffffu; } }
+    atomicAdd(&s_nk, mine);
+    __syncthreads();
+    int const nk = s_nk;
+    // search_topscores: count >= min(minwordmatches, kmersamplecount)  (searchcore.cpp:320)
+    uint32_t const minmatches = static_cast<uint32_t>(minwordmatches < nk ? minwordmatches : nk);
+
+    for (int sh = 0; sh < nshards; sh++) {
+      ShardDev const S = shards[sh];
+      // 2. zero the counters; fetch the bounds of every k-mer's posting list in this shard
+      for (int i = threadIdx.x; i < SHARD / 2; i += blockDim.x) { counters[i] = 0; }
+      for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+        uint32_t const km = kmers[i];
+        uint32_t b = 0, n = 0;
+        if (km != 0xffffffffu) { b = S.start[km]; n = S.start[km + 1] - b; }
+        lbeg[i] = b; llen[i] = n;
+      }
+      __syncthreads();
+      // 3. postings -> counters, one warp per list (targets within a list are distinct)
+      for (int i = warp; i < np2; i += NWARPS) {
+        uint32_t const n = llen[i];
+        const uint16_t * __restrict__ pl = S.post + lbeg[i];
+        for (uint32_t e = lane; e < n; e += 32) {
+          uint32_t const t = pl[e];
+          atomicAdd(&counters[t >> 1], (t & 1) ? 0x10000u : 1u);
+        }
+      }
+      __syncthreads();
+      // 4. threshold scan in segments; sort-and-cut the candidate list when it could overflow
+      int const nwords = (S.nt + 1) >> 1;
+      for (int seg = 0; seg < nwords; seg += SCAN_SEG_WORDS) {
+        if (s_ncand + 2 * SCAN_SEG_WORDS > CAND_CAP) {
+          int const m = s_ncand;
+          int const p2 = next_pow2(m);
+          for (int i = m + threadIdx.x; i < p2; i += blockDim.x) { cand[i] = 0; }
+          bitonic_sort_shared<uint64_t, true>(cand, p2);
+          if (threadIdx.x == 0) { s_ncand = m < tophits ? m : tophits; }
+          __syncthreads();
+        }
+        int const wend = min(seg + SCAN_SEG_WORDS, nwords);
+        for (int wi = seg + threadIdx.x; wi < wend; wi += blockDim.x) {
+          uint32_t const w = counters[wi];
+          uint32_t const c0 = w & 0xffffu, c1 = w >> 16;
+          int const lt0 = 2 * wi, lt1 = 2 * wi + 1;
+          if (c0 >= minmatches && lt0 < S.nt) {
+            int const t = S.t0 + lt0;
+            cand[atomicAdd(&s_ncand, 1)] = make_key(c0, static_cast<uint32_t>(db.len[t]), static_cast<uint32_t>(t));
+          }
+          if (c1 >= minmatches && lt1 < S.nt) {
+            int const t = S.t0 + lt1;
+            cand[atomicAdd(&s_ncand, 1)] = make_key(c1, static_cast<uint32_t>(db.len[t]), static_cast<uint32_t>(t));
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // 5. final order
+    int const m = s_ncand;
+    int const p2 = next_pow2(m > 1 ? m : 1);
+    for (int i = m + threadIdx.x; i < p2; i += blockDim.x) { cand[i] = 0; }
+    bitonic_sort_shared<uint64_t, true>(cand, p2);
+    int const nout = m < tophits ? m : tophits;
+    for (int i = threadIdx.x; i < nout; i += blockDim.x) {
+      uint64_t const key = cand[i];
+      out_seqno[static_cast<size_t>(qi) * tophits + i] = 0xffffffu - static_cast<uint32_t>(key & 0xffffffu);
+      out_count[static_cast<size_t>(qi) * tophits + i] = static_cast<uint32_t>(key >> 49);
+    }
+    if (threadIdx.x == 0) { out_n[qi] = nout; }
+    __syncthreads();
+  }
+}
+
+constexpr size_t RANK_SMEM = SHARD * 2 + CAND_CAP * 8 + KMER_CAP * 4 * 3;
+
+}  // namespace vsg
+
 using namespace vsg;
-struct vsg_index { int dummy; };
-extern "C" int vsg_index_create(vsg_ctx *, const vsg_seqset *, int, int, vsg_index ** out)
-{ if (out) { *out = nullptr; } Error::set("vsg_index_create: not implemented yet"); return VSG_EINVAL; }
-extern "C" void vsg_index_destroy(vsg_index *) {}
-extern "C" int vsg_rank(vsg_ctx *, const vsg_index *, const vsg_seqset *, int64_t, int64_t, int, int, int,
-                        uint32_t *, uint32_t *, int32_t *)
-{ Error::set("vsg_rank: not implemented yet"); return VSG_EINVAL; }
+
+struct vsg_index {
+  int device = 0;
+  int k = 8;
+  int mask_lower = 0;
+  int64_t ntargets = 0;
+  const vsg_seqset * db = nullptr;
+  std::vector<DevBuf> b_start, b_post;
+  std::vector<ShardDev> h_shards;
+  DevBuf b_shards;
+  int64_t total_postings = 0;
+};
+
+extern "C" int vsg_index_create(vsg_ctx * c, const vsg_seqset * db, int wordlength, int mask_lower,
+                                vsg_index ** out)
+{
+  if (c == nullptr || db == nullptr || out == nullptr) { Error::set("vsg_index_create: null argument"); return VSG_EINVAL; }
+  *out = nullptr;
+  if (wordlength < 3 || wordlength > 10) {
+    Error::set("vsg_index_create: the device index supports --wordlength 3..10 (reference: 3..15)");
+    return VSG_EINVAL;
+  }
+  if (db->d.n > (1 << 24)) { Error::set("vsg_index_create: more than 2^24 targets"); return VSG_EINVAL; }
+  VSG_CUDA_OK(cudaSetDevice(c->device));
+  vsg_index * ix = new (std::nothrow) vsg_index();
+  if (ix == nullptr) { Error::set("out of host memory"); return VSG_ENOMEM; }
+  ix->device = c->device; ix->k = wordlength; ix->mask_lower = mask_lower; ix->ntargets = db->d.n; ix->db = db;
+  int const k = wordlength;
+  size_t const hashsize = static_cast<size_t>(1) << (2 * k);
+  size_t const bitmap_bytes = std::max<size_t>(hashsize / 8, 4);
+  if (bitmap_bytes > 48 * 1024) {
+    VSG_CUDA_OK(cudaFuncSetAttribute(index_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bitmap_bytes)));
+    VSG_CUDA_OK(cudaFuncSetAttribute(index_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bitmap_bytes)));
+  }
+  int const nshards = static_cast<int>((db->d.n + SHARD - 1) / SHARD);
+  ix->b_start.resize(static_cast<size_t>(nshards));
+  ix->b_post.resize(static_cast<size_t>(nshards));
+  DevBuf cnt, tmp;
+  int rc;
+  if ((rc = cnt.reserve(sizeof(uint32_t) * (hashsize + 1))) != VSG_OK) { vsg_index_destroy(ix); return rc; }
+  for (int sh = 0; sh < nshards; sh++) {
+    int const t0 = sh * SHARD;
+    int const nt = static_cast<int>(std::min<int64_t>(SHARD, db->d.n - t0));
+    DevBuf & bs = ix->b_start[static_cast<size_t>(sh)];
+    if ((rc = bs.reserve(sizeof(uint32_t) * (hashsize + 1))) != VSG_OK) { vsg_index_destroy(ix); return rc; }
+    VSG_CUDA_OK(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * (hashsize + 1), c->stream));
+    index_build_kernel<false><<<nt, 128, bitmap_bytes, c->stream>>>(db->d, t0, nt, k, mask_lower,
+                                                                    static_cast<uint32_t *>(cnt.p), nullptr, nullptr);
+    count_launch();
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, static_cast<uint32_t *>(cnt.p), static_cast<uint32_t *>(bs.p),
+                                  static_cast<int>(hashsize + 1), c->stream);
+    if ((rc = tmp.reserve(tb + 16)) != VSG_OK) { vsg_index_destroy(ix); return rc; }
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, static_cast<uint32_t *>(cnt.p), static_cast<uint32_t *>(bs.p),
+                                  static_cast<int>(hashsize + 1), c->stream);
+    count_launch();
+    uint32_t total = 0;
+    VSG_CUDA_OK(cudaMemcpyAsync(&total, static_cast<uint32_t *>(bs.p) + hashsize, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+    DevBuf & bp = ix->b_post[static_cast<size_t>(sh)];
+    if ((rc = bp.reserve(sizeof(uint16_t) * (static_cast<size_t>(total) + 64))) != VSG_OK) { vsg_index_destroy(ix); return rc; }
+    VSG_CUDA_OK(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * (hashsize + 1), c->stream));
+    index_build_kernel<true><<<nt, 128, bitmap_bytes, c->stream>>>(db->d, t0, nt, k, mask_lower,
+                                                                   static_cast<uint32_t *>(cnt.p),
+                                                                   static_cast<uint32_t *>(bs.p),
+                                                                   static_cast<uint16_t *>(bp.p));
+    count_launch();
+    ShardDev sd;
+    sd.start = static_cast<uint32_t *>(bs.p); sd.post = static_cast<uint16_t *>(bp.p); sd.t0 = t0; sd.nt = nt;
+    ix->h_shards.push_back(sd);
+    ix->total_postings += total;
+  }
+  if ((rc = ix->b_shards.reserve(sizeof(ShardDev) * (ix->h_shards.size() + 1))) != VSG_OK) { vsg_index_destroy(ix); return rc; }
+  if (!ix->h_shards.empty()) {
+    VSG_CUDA_OK(cudaMemcpyAsync(ix->b_shards.p, ix->h_shards.data(), sizeof(ShardDev) * ix->h_shards.size(), cudaMemcpyHostToDevice, c->stream));
+  }
+  VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+  VSG_CUDA_OK(cudaGetLastError());
+  cnt.release(); tmp.release();
+  *out = ix;
+  return VSG_OK;
+}
+
+extern "C" void vsg_index_destroy(vsg_index * ix)
+{
+  if (ix == nullptr) { return; }
+  cudaSetDevice(ix->device);
+  for (auto & b : ix->b_start) { b.release(); }
+  for (auto & b : ix->b_post) { b.release(); }
+  ix->b_shards.release();
+  delete ix;
+}
+
+namespace vsg {
+const vsg_seqset * index_db(const vsg_index * ix) { return ix->db; }
+int index_wordlength(const vsg_index * ix) { return ix->k; }
+
+// device-side results left in ctx->rank_tmp: [seqno nq*tophits][count nq*tophits][n nq][status 1]
+int rank_enqueue(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * queries, int64_t q0, int64_t nq,
+                 int minwordmatches, int tophits, int mask_lower, uint32_t ** d_seqno, uint32_t ** d_count,
+                 int32_t ** d_n, int32_t ** d_status)
+{
+  if (tophits < 1 || tophits > TOPHITS_MAX) { Error::set("vsg_rank: tophits must be in 1..1024"); return VSG_EINVAL; }
+  if (q0 < 0 || nq < 0 || q0 + nq > queries->d.n) { Error::set("vsg_rank: query range out of bounds"); return VSG_EINVAL; }
+  if (nq > (1 << 30) / tophits) { Error::set("vsg_rank: batch too large"); return VSG_EINVAL; }
+  size_t const cells = static_cast<size_t>(nq) * tophits;
+  int rc;
+  if ((rc = c->rank_tmp.reserve(sizeof(uint32_t) * (2 * cells + nq + 4))) != VSG_OK) { return rc; }
+  *d_seqno = static_cast<uint32_t *>(c->rank_tmp.p);
+  *d_count = *d_seqno + cells;
+  *d_n = reinterpret_cast<int32_t *>(*d_count + cells);
+  *d_status = *d_n + nq;
+  VSG_CUDA_OK(cudaMemsetAsync(*d_status, 0, sizeof(int32_t), c->stream));
+  if (nq == 0) { return VSG_OK; }
+  VSG_CUDA_OK(cudaFuncSetAttribute(rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(RANK_SMEM)));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  int const grid = static_cast<int>(std::min<int64_t>(nq, static_cast<int64_t>(sms) * 2));
+  rank_kernel<<<grid, RANK_THREADS, RANK_SMEM, c->stream>>>(
+      queries->d, q0, static_cast<int>(nq), ix->db->d, static_cast<const ShardDev *>(ix->b_shards.p),
+      static_cast<int>(ix->h_shards.size()), ix->k, mask_lower, minwordmatches, tophits, *d_seqno, *d_count, *d_n,
+      *d_status);
+  count_launch();
+  return VSG_OK;
+}
+}  // namespace vsg
+
+extern "C" int vsg_rank(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * queries, int64_t q0, int64_t nq,
+                        int minwordmatches, int tophits, int mask_lower, uint32_t * cand_seqno,
+                        uint32_t * cand_count, int32_t * ncand)
+{
+  if (c == nullptr || ix == nullptr || queries == nullptr || cand_seqno == nullptr || cand_count == nullptr || ncand == nullptr) {
+    Error::set("vsg_rank: null argument");
+    return VSG_EINVAL;
+  }
+  VSG_CUDA_OK(cudaSetDevice(c->device));
+  uint32_t *d_seqno, *d_count; int32_t *d_n, *d_status;
+  int rc = rank_enqueue(c, ix, queries, q0, nq, minwordmatches, tophits, mask_lower, &d_seqno, &d_count, &d_n, &d_status);
+  if (rc != VSG_OK) { return rc; }
+  size_t const cells = static_cast<size_t>(nq) * tophits;
+  int32_t status = 0;
+  if (nq > 0) {
+    VSG_CUDA_OK(cudaMemcpyAsync(cand_seqno, d_seqno, sizeof(uint32_t) * cells, cudaMemcpyDeviceToHost, c->stream));
+    VSG_CUDA_OK(cudaMemcpyAsync(cand_count, d_count, sizeof(uint32_t) * cells, cudaMemcpyDeviceToHost, c->stream));
+    VSG_CUDA_OK(cudaMemcpyAsync(ncand, d_n, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, c->stream));
+  }
+  VSG_CUDA_OK(cudaMemcpyAsync(&status, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+  VSG_CUDA_OK(cudaGetLastError());
+  if (status != 0) {
+    Error::set("vsg_rank: a query is longer than the device ranker supports (2047 + wordlength nt)");
+    return VSG_EINVAL;
+  }
+  return VSG_OK;
+}

@@ -1,11 +1,326 @@
-// search.cu — placeholder until the search driver lands (next commit): fails loudly.
+// search.cu — the per-query accept/reject driver on top of the device ranker and aligner.
+//
+// Replaces search_batch (reference core/search.hpp:135-145, core/search.cpp:397-593), i.e. for every
+// query: search_onequery (core/searchcore.cpp:884-957) -> align_delayed (:740-881) -> align_trim
+// (:343-464) -> search_acceptable_aligned (:664-737) -> search_joinhits (:1028-1052).
+//
+// The reference walks one query at a time and aligns its candidates in groups of MAXDELAYED = 8
+// (searchcore.hpp:71).  Here every query of a batch advances in lock step: each ROUND gathers, for
+// all still-active queries, exactly the group of <= 8 candidates the reference would hand to search16
+// next, aligns all groups of the round in one batched device call, and then replays the reference's
+// sequential accept/reject bookkeeping on the results.  The set of pairs aligned, the order in which
+// hits are examined and every counter are those of the reference, so the hit tables are identical.
 #include "vsg_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace vsg {
+int rank_enqueue(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * queries, int64_t q0, int64_t nq,
+                 int minwordmatches, int tophits, int mask_lower, uint32_t ** d_seqno, uint32_t ** d_count,
+                 int32_t ** d_n, int32_t ** d_status);
+int seqset_revcomp(vsg_ctx * c, const vsg_seqset * src, int64_t q0, int64_t nq, vsg_seqset ** out);
+const vsg_seqset * index_db(const vsg_index * ix);
+int index_wordlength(const vsg_index * ix);
+}  // namespace vsg
+
 using namespace vsg;
+
+namespace {
+
+constexpr int MAXDELAYED = 8;  // searchcore.hpp:71
+// searchcore.hpp:75-76
+constexpr int minwordmatches_defaults[16] = {-1, -1, -1, 18, 17, 16, 15, 14, 12, 11, 10, 9, 8, 7, 5, 3};
+
+struct Hit {  // the fields of struct hit (searchcore.hpp:78-126) this path needs
+  int target = 0, strand = 0;
+  unsigned count = 0;
+  bool accepted = false, rejected = false, aligned = false, weak = false;
+  int nwscore = 0, nwdiff = 0, nwgaps = 0, nwindels = 0, nwalignmentlength = 0;
+  int matches = 0, mismatches = 0;
+  int internal_alignmentlength = 0, internal_gaps = 0, internal_indels = 0;
+  int trim_q_left = 0, trim_q_right = 0, trim_t_left = 0, trim_t_right = 0;
+  double id = 0, id0 = 0, id1 = 0, id2 = 0, id3 = 0, id4 = 0;
+  int shortest = 0, longest = 0;
+};
+
+struct QState {
+  int ncand = 0, next = 0;
+  const uint32_t * cs = nullptr;
+  const uint32_t * cc = nullptr;
+  int hit_base = 0;  // index of this state's first Hit in the batch-wide hit array
+  int hit_count = 0, accepts = 0, rejects = 0, finalized = 0, delayed = 0;
+  bool done = false, waiting = false;
+};
+
+// align_trim's arithmetic (searchcore.cpp:409-463) from the first/last CIGAR run
+void finish_hit(Hit & h, const int32_t * trims, int iddef)
+{
+  h.trim_q_left = trims[0]; h.trim_t_left = trims[1]; h.trim_q_right = trims[2]; h.trim_t_right = trims[3];
+  if (h.trim_q_left >= h.nwalignmentlength) { h.trim_q_right = 0; }
+  if (h.trim_t_left >= h.nwalignmentlength) { h.trim_t_right = 0; }
+  int const tr = h.trim_q_left + h.trim_t_left + h.trim_q_right + h.trim_t_right;
+  h.internal_alignmentlength = h.nwalignmentlength - tr;
+  h.internal_indels = h.nwindels - tr;
+  h.internal_gaps = h.nwgaps - ((h.trim_q_left + h.trim_t_left) > 0 ? 1 : 0) - ((h.trim_q_right + h.trim_t_right) > 0 ? 1 : 0);
+  h.id0 = h.shortest > 0 ? 100.0 * h.matches / h.shortest : 0.0;
+  h.id1 = h.nwalignmentlength > 0 ? 100.0 * h.matches / h.nwalignmentlength : 0.0;
+  h.id2 = h.internal_alignmentlength > 0 ? 100.0 * h.matches / h.internal_alignmentlength : 0.0;
+  h.id3 = std::max(0.0, 100.0 * (1.0 - (1.0 * (h.mismatches + h.nwgaps) / h.longest)));
+  h.id4 = h.nwalignmentlength > 0 ? 100.0 * h.matches / h.nwalignmentlength : 0.0;
+  switch (iddef) {
+    case 0: h.id = h.id0; break; case 1: h.id = h.id1; break; case 2: h.id = h.id2; break;
+    case 3: h.id = h.id3; break; default: h.id = h.id4; break;
+  }
+}
+
+// search_acceptable_aligned with every optional filter at its default (searchcore.cpp:664-737)
+bool acceptable_aligned(Hit & h, double opt_id, double opt_weak_id)
+{
+  double const mid = 100.0 * h.matches / (h.matches + h.mismatches);  // 0/0 -> NaN fails the test, as in the reference
+  if (h.id >= 100.0 * opt_weak_id && mid >= 0.0 && h.id <= 100.0 * 1.0) {
+    if (h.id >= 100.0 * opt_id) { h.accepted = true; h.weak = false; return true; }
+    h.rejected = true; h.weak = true; return false;
+  }
+  h.rejected = true; h.weak = false; return false;
+}
+
+// hit_compare_byid (searchcore.cpp:133-179)
+bool hit_less(const Hit & a, const Hit & b)
+{
+  if (a.rejected != b.rejected) { return a.rejected < b.rejected; }
+  if (a.aligned != b.aligned) { return a.aligned > b.aligned; }
+  if (!a.aligned) { return false; }
+  if (a.id != b.id) { return a.id > b.id; }
+  return a.target < b.target;
+}
+
+}  // namespace
+
 extern "C" void vsg_search_opts_default(vsg_search_opts * o)
 {
+  if (o == nullptr) { return; }
   o->id = 0.0; o->weak_id = 10.0; o->maxaccepts = 1; o->maxrejects = 32; o->wordlength = 8;
   o->minwordmatches = -1; o->iddef = 2; o->strand_both = 0; o->mask_lower = 0; o->reserved = 0;
 }
-extern "C" int vsg_search_batch(vsg_ctx *, const vsg_index *, const vsg_seqset *, const vsg_seqset *, int64_t,
-                                int64_t, const vsg_search_opts *, vsg_search_result *, int, int32_t *, int64_t *)
-{ Error::set("vsg_search_batch: not implemented yet"); return VSG_EINVAL; }
+
+extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * db,
+                                const vsg_seqset * queries, int64_t q0, int64_t nq,
+                                const vsg_search_opts * opts, vsg_search_result * results, int max_results,
+                                int32_t * counts, int64_t * work)
+{
+  if (c == nullptr || ix == nullptr || db == nullptr || queries == nullptr || opts == nullptr ||
+      results == nullptr || counts == nullptr || max_results < 1) {
+    Error::set("vsg_search_batch: bad argument");
+    return VSG_EINVAL;
+  }
+  if (index_db(ix) != db) { Error::set("vsg_search_batch: index was built for another sequence set"); return VSG_EINVAL; }
+  if (q0 < 0 || nq < 0 || q0 + nq > queries->d.n) { Error::set("vsg_search_batch: query range out of bounds"); return VSG_EINVAL; }
+  if (opts->wordlength != index_wordlength(ix)) { Error::set("vsg_search_batch: wordlength differs from the index"); return VSG_EINVAL; }
+  if (opts->iddef < 0 || opts->iddef > 4) { Error::set("vsg_search_batch: iddef must be 0..4"); return VSG_EINVAL; }
+
+  // option fix-ups: vsearch_apply_defaults_fixups (vsearch.cc:186-276) and the seqcount clamps of
+  // search_prep / search_session_init (commands/usearch_global.cpp:598-614)
+  int64_t const seqcount = db->d.n;
+  int64_t maxaccepts = opts->maxaccepts, maxrejects = opts->maxrejects < 0 ? 32 : opts->maxrejects;
+  if (maxaccepts < 0) { Error::set("vsg_search_batch: maxaccepts must not be negative"); return VSG_EINVAL; }
+  if (maxaccepts > seqcount || maxaccepts == 0) { maxaccepts = seqcount; }
+  if (maxrejects > seqcount || maxrejects == 0) { maxrejects = seqcount; }
+  int64_t tophits64 = maxaccepts + maxrejects + MAXDELAYED;
+  if (tophits64 > seqcount) { tophits64 = seqcount; }
+  int const minwordmatches = opts->minwordmatches < 0 ? minwordmatches_defaults[opts->wordlength] : opts->minwordmatches;
+  double const opt_id = opts->id;
+  double const opt_weak_id = (opts->id >= 0.0 && opts->weak_id > opts->id) ? opts->id : opts->weak_id;
+  int64_t total_pairs = 0, total_cells = 0;
+  for (int64_t q = 0; q < nq; q++) { counts[q] = 0; }
+  if (seqcount == 0 || nq == 0) { if (work) { work[0] = 0; work[1] = 0; } return VSG_OK; }
+  if (tophits64 > 1024) { Error::set("vsg_search_batch: maxaccepts+maxrejects+8 > 1024 is not supported on the device ranker"); return VSG_EINVAL; }
+  int const tophits = static_cast<int>(tophits64);
+  int const nstrands = opts->strand_both ? 2 : 1;
+
+  int64_t const BATCH = 32768;
+  std::vector<uint32_t> h_seqno, h_count;
+  std::vector<int32_t> h_n;
+  std::vector<QState> st;
+  std::vector<Hit> hits;
+  std::vector<uint32_t> pq, pt;
+  std::vector<int> pstate;  // which state each pair belongs to
+  std::vector<int16_t> a_score;
+  std::vector<uint16_t> a_al, a_ma, a_mi, a_ga;
+  std::vector<int32_t> a_tr;
+  std::vector<Hit> joined;
+
+  for (int64_t b0 = 0; b0 < nq; b0 += BATCH) {
+    int64_t const bn = std::min(BATCH, nq - b0);
+    vsg_seqset * rc_set = nullptr;
+    if (nstrands == 2) {
+      int const r = seqset_revcomp(c, queries, q0 + b0, bn, &rc_set);
+      if (r != VSG_OK) { return r; }
+    }
+    size_t const cells = static_cast<size_t>(bn) * tophits;
+    h_seqno.resize(cells * nstrands); h_count.resize(cells * nstrands); h_n.resize(static_cast<size_t>(bn) * nstrands);
+    for (int s = 0; s < nstrands; s++) {
+      uint32_t *d_seqno, *d_count; int32_t *d_n, *d_status;
+      const vsg_seqset * qset = (s == 0) ? queries : rc_set;
+      int64_t const qq0 = (s == 0) ? q0 + b0 : 0;
+      int r = rank_enqueue(c, ix, qset, qq0, bn, minwordmatches, tophits, opts->mask_lower, &d_seqno, &d_count, &d_n, &d_status);
+      if (r != VSG_OK) { if (rc_set) { vsg_seqset_destroy(rc_set); } return r; }
+      int32_t status = 0;
+      VSG_CUDA_OK(cudaMemcpyAsync(h_seqno.data() + cells * s, d_seqno, sizeof(uint32_t) * cells, cudaMemcpyDeviceToHost, c->stream));
+      VSG_CUDA_OK(cudaMemcpyAsync(h_count.data() + cells * s, d_count, sizeof(uint32_t) * cells, cudaMemcpyDeviceToHost, c->stream));
+      VSG_CUDA_OK(cudaMemcpyAsync(h_n.data() + bn * s, d_n, sizeof(int32_t) * bn, cudaMemcpyDeviceToHost, c->stream));
+      VSG_CUDA_OK(cudaMemcpyAsync(&status, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+      VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+      if (status != 0) {
+        if (rc_set) { vsg_seqset_destroy(rc_set); }
+        Error::set("vsg_search_batch: a query is longer than the device ranker supports (2047 + wordlength nt)");
+        return VSG_EINVAL;
+      }
+    }
+
+    // one state per (query, strand); hits preallocated at tophits per state
+    st.assign(static_cast<size_t>(bn) * nstrands, QState());
+    hits.assign(static_cast<size_t>(bn) * nstrands * tophits, Hit());
+    for (int s = 0; s < nstrands; s++) {
+      for (int64_t q = 0; q < bn; q++) {
+        QState & S = st[static_cast<size_t>(s) * bn + q];
+        S.ncand = h_n[static_cast<size_t>(s) * bn + q];
+        S.cs = h_seqno.data() + cells * s + static_cast<size_t>(q) * tophits;
+        S.cc = h_count.data() + cells * s + static_cast<size_t>(q) * tophits;
+        S.hit_base = static_cast<int>((static_cast<size_t>(s) * bn + q) * tophits);
+      }
+    }
+
+    bool any = true;
+    while (any) {
+      any = false;
+      pq.clear(); pt.clear(); pstate.clear();
+      // gather: run each active query's candidate loop up to its next align_delayed (searchcore.cpp:915-954)
+      for (size_t si = 0; si < st.size(); si++) {
+        QState & S = st[si];
+        if (S.done) { continue; }
+        bool trigger = false;
+        while ((S.finalized + S.delayed < maxaccepts + maxrejects - 1) && (S.rejects < maxrejects) &&
+               (S.accepts < maxaccepts) && (S.next < S.ncand)) {
+          Hit & h = hits[static_cast<size_t>(S.hit_base) + S.hit_count];
+          h = Hit();
+          h.target = static_cast<int>(S.cs[S.next]); h.count = S.cc[S.next];
+          h.strand = static_cast<int>(si / static_cast<size_t>(bn));
+          S.next++;
+          S.delayed++;  // search_acceptable_unaligned: default filters pass every candidate
+          S.hit_count++;
+          if (S.delayed == MAXDELAYED) { trigger = true; break; }
+        }
+        if (!trigger && S.delayed == 0) { S.done = true; continue; }
+        // align_delayed's search16 call: every not-yet-finalized, not pre-rejected hit
+        int const strand = static_cast<int>(si / static_cast<size_t>(bn));
+        int64_t const ql = static_cast<int64_t>(si % static_cast<size_t>(bn));
+        for (int x = S.finalized; x < S.hit_count; x++) {
+          Hit const & h = hits[static_cast<size_t>(S.hit_base) + x];
+          if (!h.rejected) {
+            pq.push_back(static_cast<uint32_t>(strand == 0 ? q0 + b0 + ql : ql));
+            pt.push_back(static_cast<uint32_t>(h.target));
+            pstate.push_back(static_cast<int>(si));
+          }
+        }
+        S.waiting = true;
+        any = true;
+      }
+      if (!any) { break; }
+      size_t const np = pq.size();
+      a_score.resize(np); a_al.resize(np); a_ma.resize(np); a_mi.resize(np); a_ga.resize(np); a_tr.resize(np * 4);
+      // pairs of the plus strand index `queries`, those of the minus strand index rc_set: two calls
+      size_t split = np;
+      if (nstrands == 2) {
+        // states are ordered plus first, minus second, so pairs are too
+        split = 0;
+        while (split < np && static_cast<int64_t>(pstate[split]) < bn) { split++; }
+      }
+      for (int part = 0; part < 2; part++) {
+        size_t const lo = part == 0 ? 0 : split, hi = part == 0 ? split : np;
+        if (hi <= lo) { continue; }
+        const vsg_seqset * qset = part == 0 ? queries : rc_set;
+        int const r = vsg_align_pairs(c, qset, db, static_cast<int64_t>(hi - lo), pq.data() + lo, pt.data() + lo,
+                                      a_score.data() + lo, a_al.data() + lo, a_ma.data() + lo, a_mi.data() + lo,
+                                      a_ga.data() + lo, a_tr.data() + 4 * lo, nullptr, 0, nullptr);
+        if (r != VSG_OK) { if (rc_set) { vsg_seqset_destroy(rc_set); } return r; }
+      }
+      total_pairs += static_cast<int64_t>(np);
+      // replay: the second half of align_delayed (searchcore.cpp:780-880)
+      size_t pi = 0;
+      for (size_t si = 0; si < st.size(); si++) {
+        QState & S = st[si];
+        if (!S.waiting) { continue; }
+        S.waiting = false;
+        int64_t const ql = static_cast<int64_t>(si % static_cast<size_t>(bn));
+        int const strand = static_cast<int>(si / static_cast<size_t>(bn));
+        int const qlen = (strand == 0 ? queries->h_len[static_cast<size_t>(q0 + b0 + ql)] : rc_set->h_len[static_cast<size_t>(ql)]);
+        size_t i = pi;
+        for (int x = S.finalized; x < S.hit_count; x++) {
+          Hit & h = hits[static_cast<size_t>(S.hit_base) + x];
+          if (!h.rejected) { total_cells += static_cast<int64_t>(qlen) * db->h_len[static_cast<size_t>(h.target)]; }
+        }
+        for (int x = S.finalized; x < S.hit_count; x++) {
+          if (S.rejects < maxrejects && S.accepts < maxaccepts) {
+            Hit & h = hits[static_cast<size_t>(S.hit_base) + x];
+            if (h.rejected) { S.rejects++; continue; }
+            if (a_score[i] == VSG_SCORE_SENTINEL) {
+              if (rc_set) { vsg_seqset_destroy(rc_set); }
+              Error::set("vsg_search_batch: a pair was deferred to the linear-memory aligner "
+                         "(core/linmemalign.cpp), which this library does not provide");
+              return VSG_EINVAL;
+            }
+            int const dlen = db->h_len[static_cast<size_t>(h.target)];
+            h.aligned = true;
+            h.shortest = std::min(qlen, dlen);
+            h.longest = std::max(qlen, dlen);
+            h.nwscore = a_score[i];
+            h.nwalignmentlength = a_al[i];
+            h.nwdiff = a_al[i] - a_ma[i];
+            h.nwgaps = a_ga[i];
+            h.nwindels = a_al[i] - a_ma[i] - a_mi[i];
+            h.matches = a_al[i] - h.nwdiff;
+            h.mismatches = h.nwdiff - h.nwindels;
+            finish_hit(h, &a_tr[4 * i], opts->iddef);
+            if (acceptable_aligned(h, opt_id, opt_weak_id)) { S.accepts++; } else { S.rejects++; }
+            ++i;
+          }
+        }
+        // the pairs of this state, examined or not, are consumed
+        size_t mine = 0;
+        while (pi + mine < np && static_cast<size_t>(pstate[pi + mine]) == si) { mine++; }
+        pi += mine;
+        S.finalized = S.hit_count;
+        S.delayed = 0;
+      }
+    }
+
+    // search_joinhits + result records (search.cpp:466-488)
+    for (int64_t q = 0; q < bn; q++) {
+      joined.clear();
+      for (int s = 0; s < nstrands; s++) {
+        QState const & S = st[static_cast<size_t>(s) * bn + q];
+        for (int x = 0; x < S.hit_count; x++) {
+          Hit const & h = hits[static_cast<size_t>(S.hit_base) + x];
+          if (h.accepted || h.weak) { joined.push_back(h); }
+        }
+      }
+      std::stable_sort(joined.begin(), joined.end(), hit_less);
+      int const n = static_cast<int>(std::min<size_t>(joined.size(), static_cast<size_t>(max_results)));
+      for (int j = 0; j < n; j++) {
+        Hit const & h = joined[static_cast<size_t>(j)];
+        vsg_search_result & r = results[static_cast<size_t>(b0 + q) * max_results + j];
+        r.target = h.target; r.matches = h.matches; r.mismatches = h.mismatches; r.gaps = h.nwgaps;
+        r.alignment_length = h.nwalignmentlength;
+        r.query_length = queries->h_len[static_cast<size_t>(q0 + b0 + q)];
+        r.target_length = db->h_len[static_cast<size_t>(h.target)];
+        r.accepted = h.accepted ? 1 : 0; r.strand = h.strand; r.nwscore = h.nwscore; r.id = h.id;
+      }
+      counts[b0 + q] = n;
+    }
+    if (rc_set) { vsg_seqset_destroy(rc_set); }
+  }
+  if (work != nullptr) { work[0] = total_pairs; work[1] = total_cells; }
+  return VSG_OK;
+}

@@ -289,6 +289,43 @@ extern "C" void vsg_seqset_destroy(vsg_seqset * s)
   delete s;
 }
 
+namespace vsg {
+int seqset_revcomp(vsg_ctx * c, const vsg_seqset * src, int64_t q0, int64_t n, vsg_seqset ** out)
+{
+  *out = nullptr;
+  vsg_seqset * s = new (std::nothrow) vsg_seqset();
+  if (s == nullptr) { Error::set("out of host memory"); return VSG_ENOMEM; }
+  s->device = c->device;
+  s->h_len.assign(src->h_len.begin() + q0, src->h_len.begin() + q0 + n);
+  s->h_nonacgt.assign(src->h_nonacgt.begin() + q0, src->h_nonacgt.begin() + q0 + n);
+  std::vector<int64_t> h_off(static_cast<size_t>(n));
+  int64_t total = 0;
+  for (int64_t i = 0; i < n; i++) { h_off[static_cast<size_t>(i)] = total; total += s->h_len[static_cast<size_t>(i)]; }
+  s->total = total;
+  int rc;
+  if ((rc = s->b_sym.reserve(static_cast<size_t>(total) + 64)) != VSG_OK ||
+      (rc = s->b_off.reserve(sizeof(int64_t) * static_cast<size_t>(n) + 8)) != VSG_OK ||
+      (rc = s->b_len.reserve(sizeof(int32_t) * static_cast<size_t>(n) + 8)) != VSG_OK) {
+    vsg_seqset_destroy(s);
+    return rc;
+  }
+  s->d.sym = static_cast<uint8_t *>(s->b_sym.p);
+  s->d.off = static_cast<int64_t *>(s->b_off.p);
+  s->d.len = static_cast<int32_t *>(s->b_len.p);
+  s->d.n = n;
+  if (n > 0) {
+    VSG_CUDA_OK(cudaMemcpyAsync(s->b_off.p, h_off.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, c->stream));
+    VSG_CUDA_OK(cudaMemcpyAsync(s->b_len.p, s->h_len.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    int64_t const blocks = (n * 32 + 255) / 256;
+    revcomp_kernel<<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(src->d, q0, n, s->d.off, static_cast<uint8_t *>(s->b_sym.p));
+    count_launch();
+    VSG_CUDA_OK(cudaStreamSynchronize(c->stream));  // h_off goes out of scope
+  }
+  *out = s;
+  return VSG_OK;
+}
+}  // namespace vsg
+
 extern "C" int64_t vsg_seqset_count(const vsg_seqset * s) { return s != nullptr ? s->d.n : 0; }
 
 // ---- the aligner -----------------------------------------------------------------------------
