@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — the hot path on BASELINE.json's headline configuration.
+
+Workload (configs[1]): --usearch_global, 250-nt queries (5 % mutated windows of database
+sequences) against a 100 000 x 1 500 nt iid database, --id 0.9, default scoring, k = 8,
+maxaccepts 1 / maxrejects 32, masking none.  One STEP = one pass of the whole hot path (k-mer
+ranking -> batched 16-bit global alignment -> traceback -> accept/reject replay) over one batch of
+`--batch` queries of that stream per GPU; per-GPU work is fixed as N grows (weak scaling), the
+database is broadcast from rank 0 over NCCL and every rank builds its index from it on device.
+
+metric = GCUPS as SURVEY.md §8(d) defines it: sum over the pairs the reference's driver hands to
+search16 of qlen*dlen, divided by time.  Our driver aligns exactly that set of pairs
+(tests/test_search_gpu.py checks the counts against the reference), so numerator and unit are the
+same for both arms.
+
+  value   inputs (database, index, query batches) already resident in HBM when the timed region starts
+  e2e     the same steps through the C ABI with HOST buffers: each step uploads its query batch from
+          pinned host memory (vsg_seqset_create) and gets its hit table back in host memory
+  --impl reference   the UNMODIFIED reference (oracle/_ref/libvsref.so: its own search_batch on all
+          host threads, workload counted by a link-time wrapper around search16) on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DB, DB_LEN, Q_LEN, DIV, SEED = 100_000, 1500, 250, 0.05, 2024
+IDENT, MAXACC, MAXREJ, K = 0.9, 1, 32, 8
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nme in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def pinned_seqset(ss):
+    """copy a SeqSet's arrays into pinned host memory (torch allocator)"""
+    import torch
+    from vsearch_b200 import synth
+    out = synth.SeqSet.__new__(synth.SeqSet)
+    for name in ("cat", "offs", "lens"):
+        a = getattr(ss, name)
+        t = torch.empty(a.shape, dtype=getattr(torch, str(a.dtype)), pin_memory=True)
+        v = t.numpy()
+        v[...] = a
+        setattr(out, name, v)
+        setattr(out, "_keep_" + name, t)
+    return out
+
+
+def reference_arm(args, rank):
+    """Times the unmodified reference on this box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import checkers
+    from vsearch_b200 import synth
+    cores = os.cpu_count() or 1
+    if checkers.ref() is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvsref.so not built"}))
+        return
+    lib = checkers.ref()
+    dbm = synth.config2_db(N_DB, DB_LEN, SEED)
+    dbs = synth.SeqSet.from_matrix(dbm)
+    t0 = time.time()
+    r = checkers.RefDb(dbs, k=K, id=IDENT, maxaccepts=MAXACC, maxrejects=MAXREJ, dust=0)
+    build_s = time.time() - t0
+    sample = args.ref_sample
+    times, cells_l, pairs_l = [], [], []
+    for step in range(args.warmup + args.steps):
+        qs, _ = synth.config2_query_batch(dbm, sample, Q_LEN, DIV, SEED, batch=step)
+        ft = np.zeros(sample, dtype=np.int32)
+        lib.vsref_work_reset()
+        t0 = time.perf_counter()
+        lib.vsref_db_search_batch(C.c_void_p(r.h), C.c_int(sample), checkers._p(qs.cat, C.c_char),
+                                  checkers._p(qs.offs, C.c_int64), checkers._p(qs.lens, C.c_int),
+                                  C.c_int(cores), checkers._p(ft, C.c_int))
+        dt = time.perf_counter() - t0
+        p = C.c_longlong(); c = C.c_longlong(); k = C.c_longlong()
+        lib.vsref_work_get(C.byref(p), C.byref(c), C.byref(k))
+        if step >= args.warmup:
+            times.append(dt); cells_l.append(c.value); pairs_l.append(p.value)
+    r.close()
+    tot = sum(times)
+    gcups = sum(cells_l) / tot / 1e9
+    line = {"impl": "reference", "metric": "usearch_global_gcups", "value": gcups, "unit": "GCUPS",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * tot / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+            "config": {"workload": "usearch_global 250nt queries vs 100k x 1500nt DB, id 0.9 (configs[1])",
+                       "queries_per_step": sample, "masking": "none", "reference_index_build_s": round(build_s, 1)},
+            "queries_per_s": sample * args.steps / tot, "pairs_per_s": sum(pairs_l) / tot,
+            "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": "reference",
+                             "sample": f"{sample} queries per step of the same stream, reference search_batch "
+                                       f"--threads {cores}"},
+            "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="vsg", choices=["vsg", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="queries per step per GPU")
+    ap.add_argument("--ref-sample", type=int, default=8192, help="queries per step of the reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="queries of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from vsearch_b200 import lib as vlib, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference "
+                         "for the reference's CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    ctx = vlib.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local))
+
+    # ---- database: rank 0 makes it; the packed bytes go to every GPU over NCCL/NVLink -------------
+    dbm = synth.config2_db(N_DB, DB_LEN, SEED)  # every rank needs the matrix to draw its queries
+    if world > 1:
+        n = N_DB
+        d_cat = torch.empty(n * DB_LEN, dtype=torch.uint8, device="cuda")
+        d_off = torch.empty(n, dtype=torch.int64, device="cuda")
+        d_len = torch.empty(n, dtype=torch.int32, device="cuda")
+        if rank == 0:
+            d_cat.copy_(torch.from_numpy(dbm.reshape(-1)))
+            d_off.copy_(torch.arange(n, dtype=torch.int64) * DB_LEN)
+            d_len.fill_(DB_LEN)
+        dist.broadcast(d_cat, 0); dist.broadcast(d_off, 0); dist.broadcast(d_len, 0)
+        torch.cuda.synchronize()
+        db = ctx.seqset_from_device(d_cat.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), n)
+    else:
+        db = ctx.seqset(synth.SeqSet.from_matrix(dbm))
+    ix = ctx.index(db, K, 0)
+
+    opts = vlib.default_search_opts()
+    opts.id = IDENT; opts.maxaccepts = MAXACC; opts.maxrejects = MAXREJ; opts.wordlength = K
+    max_results = 1
+
+    nsteps = args.warmup + args.steps
+    batches = []
+    for step in range(nsteps):
+        qs, _ = synth.config2_query_batch(dbm, args.batch, Q_LEN, DIV, SEED, batch=step * world + rank)
+        batches.append(pinned_seqset(qs))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(e2e: bool):
+        """returns (device ms for the K timed steps, work, launches, profile, clocks)"""
+        handles = None
+        if not e2e:
+            handles = [ctx.seqset(b) for b in batches]
+        work_tot = np.zeros(2, dtype=np.int64)
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        sampler = None
+        launches0 = 0
+        for step in range(nsteps):
+            if step == args.warmup:
+                barrier()
+                sampler = ClockSampler(local); sampler.start()
+                ctx.profile_reset()
+                launches0 = vlib.launch_count()
+                ev0.record(stream)
+            h = ctx.seqset(batches[step]) if e2e else handles[step]
+            res, counts, work = ctx.search(ix, db, h, 0, args.batch, opts, max_results)
+            if e2e:
+                h.close()
+            if step >= args.warmup:
+                work_tot += work
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        clocks = sampler.summary() if sampler else {}
+        prof = ctx.profile()
+        launches = vlib.launch_count() - launches0
+        hits = int((counts > 0).sum())
+        if handles:
+            for hh in handles:
+                hh.close()
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            w = torch.tensor(work_tot, dtype=torch.int64, device="cuda")
+            dist.all_reduce(w, op=dist.ReduceOp.SUM)
+            work_tot = w.cpu().numpy()
+        return ms, work_tot, launches, prof, clocks, hits
+
+    ms_dev, work_dev, launches, prof, clocks, hits = run_steps(e2e=False)
+    ms_e2e, work_e2e, _, _, _, _ = run_steps(e2e=True)
+
+    value = work_dev[1] / (ms_dev * 1e-3) / 1e9
+    e2e_value = work_e2e[1] / (ms_e2e * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (forward DP): integer-ALU bound -------------------------
+    peak_ops = ctx.int_peak()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    fwd_gcups = prof.cells / (prof.fwd_ms * 1e-3) / 1e9 if prof.fwd_ms > 0 else 0.0
+    int_peak_gcups = 2.0 * peak_ops / 15.0 / 1e9   # 2 cells per packed op, 15 ops per cell (align_simd.cpp:765-780)
+    dir_bytes_per_cell = 0.5 * (DB_LEN + 31) / DB_LEN * 256 / 250   # 4 bits/cell + wavefront and row padding
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = {"bound": "int_alu", "kernel": "nw_fast_kernel<8,false>",
+                "achieved": fwd_gcups, "peak": int_peak_gcups, "unit": "GCUPS", "frac": fwd_gcups / int_peak_gcups,
+                "peak_source": "vsg_measure_int_peak (VIMNMX.S16x2+VIADD.16x2 lane-ops/s, measured live) x2 cells /15 ops",
+                "packed_lane_ops_per_s": peak_ops,
+                "avg_launch_ms": prof.fwd_ms / max(1, prof.fwd_launches), "launches": int(prof.fwd_launches),
+                "hbm": {"achieved_gbs": fwd_gcups * dir_bytes_per_cell, "peak_gbs": hbm_peak,
+                        "frac": fwd_gcups * dir_bytes_per_cell / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
+                        "algorithmic_bytes_per_cell": dir_bytes_per_cell},
+                "traffic": None,
+                "kernel_ms": {"forward": prof.fwd_ms, "traceback": prof.traceback_ms, "rank": prof.rank_ms}}
+
+    # ---- cpu_baseline: the unmodified reference on this box's cores, bounded sample ---------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import checkers
+        cores = os.cpu_count() or 1
+        sample = args.cpu_sample
+        qs, _ = synth.config2_query_batch(dbm, sample, Q_LEN, DIV, SEED, batch=0)
+        if checkers.ref() is not None:
+            rlib = checkers.ref()
+            r = checkers.RefDb(synth.SeqSet.from_matrix(dbm), k=K, id=IDENT, maxaccepts=MAXACC, maxrejects=MAXREJ, dust=0)
+            ft = np.zeros(sample, dtype=np.int32)
+            rlib.vsref_work_reset()
+            t0 = time.perf_counter()
+            rlib.vsref_db_search_batch(C.c_void_p(r.h), C.c_int(sample), checkers._p(qs.cat, C.c_char),
+                                       checkers._p(qs.offs, C.c_int64), checkers._p(qs.lens, C.c_int),
+                                       C.c_int(cores), checkers._p(ft, C.c_int))
+            dt = time.perf_counter() - t0
+            p = C.c_longlong(); c = C.c_longlong(); k = C.c_longlong()
+            rlib.vsref_work_get(C.byref(p), C.byref(c), C.byref(k))
+            r.close()
+            cpu_baseline = {"value": c.value / dt / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference",
+                            "sample": f"first {sample} queries of batch 0, reference search_batch --threads {cores}, "
+                                      f"{dt:.1f} s", "queries_per_s": sample / dt}
+        else:
+            od = checkers.OracleDb(synth.SeqSet.from_matrix(dbm))
+            oo = checkers.search_opts(N_DB, id=IDENT, maxaccepts=MAXACC, maxrejects=MAXREJ)
+            nsm = min(sample, 64)
+            t0 = time.perf_counter(); cells = 0
+            for i in range(nsm):
+                _, _, cl = od.search(qs.seq(i), oo); cells += cl
+            dt = time.perf_counter() - t0
+            cpu_baseline = {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "port",
+                            "sample": f"first {nsm} queries of batch 0, scalar oracle"}
+
+    if rank == 0:
+        qbytes = int(np.mean([b.cat.nbytes + b.offs.nbytes + b.lens.nbytes for b in batches]))
+        rbytes = args.batch * (max_results * 48 + 4) + 16
+        line = {"metric": "usearch_global_gcups", "value": value, "unit": "GCUPS", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
+                "data": "synthetic",
+                "config": {"workload": "usearch_global 250nt queries vs 100k x 1500nt DB, id 0.9 (configs[1])",
+                           "queries_per_step_per_gpu": args.batch, "global_queries_per_step": args.batch * world,
+                           "masking": "none", "wordlength": K, "maxaccepts": MAXACC, "maxrejects": MAXREJ,
+                           "parallelism": f"query-sharded x{world}, DB NCCL-broadcast",
+                           "l2": "per-step working set (index 300 MB + direction blocks > 10 GB) exceeds the 126 MB L2"},
+                "queries_per_s": args.batch * world * args.steps / (ms_dev * 1e-3),
+                "pairs_per_s": float(work_dev[0]) / (ms_dev * 1e-3),
+                "hit_fraction_last_step": hits / args.batch,
+                "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": qbytes,
+                        "d2h_bytes_per_step": rbytes, "ms_per_step": ms_e2e / args.steps,
+                        "queries_per_s": args.batch * world * args.steps / (ms_e2e * 1e-3)},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    ix.close(); db.close(); ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

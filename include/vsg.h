@@ -99,10 +99,25 @@ int vsg_align_pairs(vsg_ctx * ctx, const vsg_seqset * queries, const vsg_seqset 
 #define VSG_STAT_CIGARLEN 7   /* strlen of the CIGAR */
 #define VSG_STAT_WORDS 8
 
-/* DP cells (sum qlen*dlen) and kernel time of the forward kernels of the last align call on this
- * context (cudaEvent, ms) — what bench.py's roofline is computed from. */
-int vsg_last_align_profile(vsg_ctx * ctx, int64_t * cells, float * fwd_ms, float * traceback_ms,
-                           int64_t * fast_pairs, int64_t * exact_pairs);
+/* Cumulative device-side profile of this context since the last vsg_profile_reset: DP cells
+ * (sum qlen*dlen of the pairs that went through a forward kernel), forward / traceback / ranker
+ * kernel time (cudaEvents on the context's stream, ms), pair counts per kernel and the number of
+ * forward launches.  bench.py computes its roofline from these. */
+typedef struct vsg_profile {
+  int64_t cells;
+  int64_t fast_pairs;
+  int64_t exact_pairs;
+  int64_t fwd_launches;
+  float fwd_ms;
+  float traceback_ms;
+  float rank_ms;
+  float reserved;
+} vsg_profile;
+int vsg_profile_reset(vsg_ctx * ctx);
+int vsg_profile_get(vsg_ctx * ctx, vsg_profile * out);
+/* Measured integer-pipe peak of this device: packed 16x2 ALU lane-operations per second
+ * (VIMNMX.S16x2 / VIADD.16x2 mix with no memory traffic), the denominator of the DP roofline. */
+int vsg_measure_int_peak(vsg_ctx * ctx, double * packed_lane_ops_per_s);
 
 /* ---- k-mer index: replaces Dbindex::prepare + add_all_sequences + the getters
  *      (core/dbindex.hpp:79-120, core/dbindex.cpp:121-255).  mask_lower != 0 means soft-masked

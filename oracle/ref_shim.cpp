@@ -26,6 +26,37 @@
 #include <vector>
 #include <memory>
 
+/* Link-time instrumentation of the UNMODIFIED reference: oracle/Makefile links libvsref.so with
+   -Wl,--wrap=<search16>, so every call the reference makes to search16 lands here first.  We only
+   count the work (pairs and DP cells = qlen*dlen handed to the SIMD aligner) and
+   pass the call through to the real function. */
+#include <atomic>
+static std::atomic<long long> g_s16_pairs{0}, g_s16_cells{0}, g_s16_calls{0};
+static thread_local int t_qlen = 0;
+extern "C" {
+void __real__Z14search16_qprepP9s16info_sPci(s16info_s *, char *, int);
+void __wrap__Z14search16_qprepP9s16info_sPci(s16info_s * s, char * q, int qlen)
+{
+  t_qlen = qlen;
+  __real__Z14search16_qprepP9s16info_sPci(s, q, qlen);
+}
+void __real__Z8search16P9s16info_sjPKjPsPtS4_S4_S4_PPcRK8Database(
+    s16info_s *, unsigned int, unsigned int const *, CELL *, unsigned short *, unsigned short *,
+    unsigned short *, unsigned short *, char **, Database const &);
+void __wrap__Z8search16P9s16info_sjPKjPsPtS4_S4_S4_PPcRK8Database(
+    s16info_s * s, unsigned int n, unsigned int const * seqnos, CELL * sc, unsigned short * a,
+    unsigned short * m, unsigned short * mm, unsigned short * g, char ** cig, Database const & db)
+{
+  long long cells = 0;
+  for (unsigned int i = 0; i < n; i++) { cells += static_cast<long long>(t_qlen) * static_cast<long long>(db.getsequencelen(seqnos[i])); }
+  g_s16_pairs += n; g_s16_cells += cells; g_s16_calls += 1;
+  __real__Z8search16P9s16info_sjPKjPsPtS4_S4_S4_PPcRK8Database(s, n, seqnos, sc, a, m, mm, g, cig, db);
+}
+void vsref_work_reset(void) { g_s16_pairs = 0; g_s16_cells = 0; g_s16_calls = 0; }
+void vsref_work_get(long long * pairs, long long * cells, long long * calls)
+{ *pairs = g_s16_pairs; *cells = g_s16_cells; *calls = g_s16_calls; }
+}
+
 namespace {
 
 struct RefDb {
@@ -212,6 +243,36 @@ void vsref_db_search(void * h, int nq, const char * qcat, const int64_t * qoff, 
   }
   search_session_cleanup(ss);
   search_session_free(ss);
+}
+
+/* the reference's own multi-threaded search_batch (core/search.cpp:511-593) on `threads` host
+   threads; returns the number of queries with at least one hit.  Results are discarded except
+   for the first hit's target (first_target[q], -1 if none): this entry point exists to TIME the
+   reference and to count its search16 workload. */
+int vsref_db_search_batch(void * h, int nq, const char * qcat, const int64_t * qoff, const int * qlen,
+                          int threads, int * first_target)
+{
+  RefDb * r = static_cast<RefDb *>(h);
+  std::vector<std::string> seqs(static_cast<size_t>(nq)), heads(static_cast<size_t>(nq));
+  std::vector<const char *> ps(static_cast<size_t>(nq)), ph(static_cast<size_t>(nq));
+  std::vector<int64_t> sizes(static_cast<size_t>(nq), 1);
+  for (int q = 0; q < nq; q++) {
+    seqs[static_cast<size_t>(q)].assign(qcat + qoff[q], static_cast<size_t>(qlen[q]));
+    heads[static_cast<size_t>(q)] = "q" + std::to_string(q);
+    ps[static_cast<size_t>(q)] = seqs[static_cast<size_t>(q)].c_str();
+    ph[static_cast<size_t>(q)] = heads[static_cast<size_t>(q)].c_str();
+  }
+  Parameters p = r->params;
+  p.opt_threads = threads;
+  std::vector<search_result_s> res(static_cast<size_t>(nq));
+  std::vector<int> counts(static_cast<size_t>(nq), 0);
+  search_batch(p, r->dbindex, r->db, ps.data(), ph.data(), qlen, sizes.data(), nq, res.data(), 1, counts.data());
+  int hits = 0;
+  for (int q = 0; q < nq; q++) {
+    first_target[q] = counts[static_cast<size_t>(q)] > 0 ? res[static_cast<size_t>(q)].target : -1;
+    hits += counts[static_cast<size_t>(q)] > 0;
+  }
+  return hits;
 }
 
 }  // extern "C"

@@ -376,12 +376,25 @@ int rank_enqueue(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * queries, 
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
   int const grid = static_cast<int>(std::min<int64_t>(nq, static_cast<int64_t>(sms) * 2));
+  VSG_CUDA_OK(cudaEventRecord(c->ev[4], c->stream));
   rank_kernel<<<grid, RANK_THREADS, RANK_SMEM, c->stream>>>(
       queries->d, q0, static_cast<int>(nq), ix->db->d, static_cast<const ShardDev *>(ix->b_shards.p),
       static_cast<int>(ix->h_shards.size()), ix->k, mask_lower, minwordmatches, tophits, *d_seqno, *d_count, *d_n,
       *d_status);
   count_launch();
+  VSG_CUDA_OK(cudaEventRecord(c->ev[5], c->stream));
+  c->rank_pending = true;
   return VSG_OK;
+}
+
+// call after the stream has been synchronised
+void rank_collect_time(vsg_ctx * c)
+{
+  if (c->rank_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) { c->prof_rank_ms += ms; }
+    c->rank_pending = false;
+  }
 }
 }  // namespace vsg
 
@@ -407,6 +420,7 @@ extern "C" int vsg_rank(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * qu
   VSG_CUDA_OK(cudaMemcpyAsync(&status, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
   VSG_CUDA_OK(cudaGetLastError());
+  rank_collect_time(c);
   if (status != 0) {
     Error::set("vsg_rank: a query is longer than the device ranker supports (2047 + wordlength nt)");
     return VSG_EINVAL;

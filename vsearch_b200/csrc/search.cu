@@ -21,6 +21,7 @@ int rank_enqueue(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * queries, 
                  int minwordmatches, int tophits, int mask_lower, uint32_t ** d_seqno, uint32_t ** d_count,
                  int32_t ** d_n, int32_t ** d_status);
 int seqset_revcomp(vsg_ctx * c, const vsg_seqset * src, int64_t q0, int64_t nq, vsg_seqset ** out);
+void rank_collect_time(vsg_ctx * c);
 const vsg_seqset * index_db(const vsg_index * ix);
 int index_wordlength(const vsg_index * ix);
 }  // namespace vsg
@@ -172,6 +173,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
       VSG_CUDA_OK(cudaMemcpyAsync(h_n.data() + bn * s, d_n, sizeof(int32_t) * bn, cudaMemcpyDeviceToHost, c->stream));
       VSG_CUDA_OK(cudaMemcpyAsync(&status, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
       VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+      rank_collect_time(c);
       if (status != 0) {
         if (rc_set) { vsg_seqset_destroy(rc_set); }
         Error::set("vsg_search_batch: a query is longer than the device ranker supports (2047 + wordlength nt)");

@@ -491,6 +491,8 @@ int run_chunk(vsg_ctx * c, const vsg_seqset * qs, const vsg_seqset * ts, Chunk &
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->prof_fwd_ms += ms;
   cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->prof_tb_ms += ms;
   c->prof_cells += ch.cells; c->prof_fast += ch.nfast; c->prof_exact += ch.nexact;
+  for (auto & g : ch.fast) { for (auto & v : g) { c->prof_fwd_launches += v.empty() ? 0 : 1; } }
+  c->prof_fwd_launches += ch.exact.empty() ? 0 : 1;
 
   // stats of this chunk's pairs: they are scattered over the slot array; copy the covering range
   int lo = INT32_MAX, hi = -1;
@@ -544,8 +546,6 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
   VSG_CUDA_OK(cudaSetDevice(c->device));
   bool const want_cigar = (cigar_buf != nullptr);
   if (want_cigar && cigar_off == nullptr) { Error::set("vsg_align_pairs: cigar_off required with cigar_buf"); return VSG_EINVAL; }
-  c->prof_cells = c->prof_fast = c->prof_exact = 0;
-  c->prof_fwd_ms = c->prof_tb_ms = 0.f;
 
   std::vector<int32_t> st(static_cast<size_t>(npairs) * VSG_STAT_WORDS, 0);
   std::vector<std::string> cigars;
@@ -693,14 +693,64 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
   return VSG_OK;
 }
 
-extern "C" int vsg_last_align_profile(vsg_ctx * c, int64_t * cells, float * fwd_ms, float * traceback_ms,
-                                      int64_t * fast_pairs, int64_t * exact_pairs)
+namespace vsg {
+// independent chains of the two packed instructions the forward kernel is made of
+__global__ void int_peak_kernel(uint32_t * out, uint32_t seed, int iters)
+{
+  uint32_t a[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { a[k] = seed * (threadIdx.x + 1) + k * 0x00030005u; }
+  uint32_t const c1 = seed | 0x00010001u, c2 = seed ^ 0x00070003u;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) { a[k] = __vmaxs2(__vadd2(a[k], c1), c2); }
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) { r ^= a[k]; }
+  if (r == 0x12345678u) { out[0] = r; }
+}
+}  // namespace vsg
+
+extern "C" int vsg_measure_int_peak(vsg_ctx * c, double * packed_lane_ops_per_s)
+{
+  if (c == nullptr || packed_lane_ops_per_s == nullptr) { return VSG_EINVAL; }
+  VSG_CUDA_OK(cudaSetDevice(c->device));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  int rc;
+  if ((rc = c->cub_tmp.reserve(64)) != VSG_OK) { return rc; }
+  int const iters = 8192, threads = 256, blocks = sms * 8;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {
+    VSG_CUDA_OK(cudaEventRecord(c->ev[4], c->stream));
+    int_peak_kernel<<<blocks, threads, 0, c->stream>>>(static_cast<uint32_t *>(c->cub_tmp.p), 3u + rep, iters);
+    count_launch();
+    VSG_CUDA_OK(cudaEventRecord(c->ev[5], c->stream));
+    VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
+    double const ops = 2.0 * 8.0 * iters * static_cast<double>(threads) * blocks;  // 2 packed ops per statement
+    if (rep > 0) { best = std::max(best, ops / (ms * 1e-3)); }
+  }
+  *packed_lane_ops_per_s = best;
+  return VSG_OK;
+}
+
+extern "C" int vsg_profile_reset(vsg_ctx * c)
 {
   if (c == nullptr) { return VSG_EINVAL; }
-  if (cells != nullptr) { *cells = c->prof_cells; }
-  if (fwd_ms != nullptr) { *fwd_ms = c->prof_fwd_ms; }
-  if (traceback_ms != nullptr) { *traceback_ms = c->prof_tb_ms; }
-  if (fast_pairs != nullptr) { *fast_pairs = c->prof_fast; }
-  if (exact_pairs != nullptr) { *exact_pairs = c->prof_exact; }
+  c->prof_cells = c->prof_fast = c->prof_exact = c->prof_fwd_launches = 0;
+  c->prof_fwd_ms = c->prof_tb_ms = c->prof_rank_ms = 0.f;
+  return VSG_OK;
+}
+
+extern "C" int vsg_profile_get(vsg_ctx * c, vsg_profile * out)
+{
+  if (c == nullptr || out == nullptr) { return VSG_EINVAL; }
+  out->cells = c->prof_cells; out->fast_pairs = c->prof_fast; out->exact_pairs = c->prof_exact;
+  out->fwd_launches = c->prof_fwd_launches;
+  out->fwd_ms = c->prof_fwd_ms; out->traceback_ms = c->prof_tb_ms; out->rank_ms = c->prof_rank_ms;
+  out->reserved = 0.f;
   return VSG_OK;
 }

@@ -38,6 +38,12 @@ class SearchOpts(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class Profile(C.Structure):
+    _fields_ = [("cells", C.c_int64), ("fast_pairs", C.c_int64), ("exact_pairs", C.c_int64),
+                ("fwd_launches", C.c_int64), ("fwd_ms", C.c_float), ("traceback_ms", C.c_float),
+                ("rank_ms", C.c_float), ("reserved", C.c_float)]
+
+
 class SearchResult(C.Structure):
     _fields_ = [("target", C.c_int32), ("matches", C.c_int32), ("mismatches", C.c_int32),
                 ("gaps", C.c_int32), ("alignment_length", C.c_int32), ("query_length", C.c_int32),
@@ -142,6 +148,22 @@ class Context:
             load().vsg_ctx_destroy(self.h)
             self.h = None
 
+    def profile_reset(self):
+        _check(load().vsg_profile_reset(self.h), "vsg_profile_reset")
+
+    def profile(self) -> Profile:
+        p = Profile()
+        _check(load().vsg_profile_get(self.h, C.byref(p)), "vsg_profile_get")
+        return p
+
+    def int_peak(self) -> float:
+        v = C.c_double()
+        _check(load().vsg_measure_int_peak(self.h, C.byref(v)), "vsg_measure_int_peak")
+        return v.value
+
+    def stream_ptr(self) -> int:
+        return int(load().vsg_ctx_stream(self.h))
+
     def sync(self):
         _check(load().vsg_ctx_sync(self.h), "vsg_ctx_sync")
 
@@ -181,6 +203,7 @@ class Context:
             cap = int((qs.lens[qidx].astype(np.int64) + ts.lens[tidx].astype(np.int64) + 2).sum()) + 16
             cbuf = np.zeros(cap, dtype=np.uint8)
             coff = np.zeros(n + 1, dtype=np.int64)
+        self.profile_reset()
         _check(lib.vsg_align_pairs(self.h, qs.h, ts.h, C.c_int64(n), _ptr(qidx, C.c_uint32),
                                    _ptr(tidx, C.c_uint32), _ptr(score, C.c_int16), _ptr(al, C.c_uint16),
                                    _ptr(ma, C.c_uint16), _ptr(mi, C.c_uint16), _ptr(ga, C.c_uint16),
@@ -190,10 +213,9 @@ class Context:
         if cigar:
             raw = cbuf.tobytes()
             cigs = [raw[int(coff[i]):int(coff[i + 1]) - 1].decode() for i in range(n)]
-        cells = C.c_int64(); f = C.c_float(); t = C.c_float(); fp = C.c_int64(); ep = C.c_int64()
-        lib.vsg_last_align_profile(self.h, C.byref(cells), C.byref(f), C.byref(t), C.byref(fp), C.byref(ep))
-        return AlignResult(score, al, ma, mi, ga, trims, cigs, cells.value, f.value, t.value,
-                           fp.value, ep.value)
+        pr = self.profile()
+        return AlignResult(score, al, ma, mi, ga, trims, cigs, pr.cells, pr.fwd_ms, pr.traceback_ms,
+                           pr.fast_pairs, pr.exact_pairs)
 
     def index(self, db: SeqSetHandle, wordlength: int = 8, mask_lower: int = 0) -> IndexHandle:
         h = C.c_void_p()

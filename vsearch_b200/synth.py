@@ -110,3 +110,53 @@ def write_fasta(path: str, ss: SeqSet, prefix: str) -> None:
     with open(path, "wb") as f:
         for i in range(len(ss)):
             f.write(b">" + prefix.encode() + str(i).encode() + b"\n" + ss.seq(i) + b"\n")
+
+
+def mutate_batch(rng: np.random.Generator, m: np.ndarray, r: float) -> SeqSet:
+    """mut(., r) applied to every row of an (n, L) ASCII matrix at once (vectorised; the draw
+    order differs from `mutate`, so the two generators give different — equally distributed —
+    sequences for the same seed)."""
+    n, L = m.shape
+    hit = rng.random((n, L)) < r
+    kind = rng.random((n, L))
+    sub = hit & (kind < 0.8)
+    dele = hit & (kind >= 0.8) & (kind < 0.9)
+    ins = hit & (kind >= 0.9)
+    out = m.copy()
+    out[sub] = ACGT[rng.integers(0, 4, size=int(sub.sum()), dtype=np.uint8)]
+    reps = np.ones((n, L), dtype=np.int64)
+    reps[dele] = 0
+    reps[ins] = 2
+    flat_reps = reps.reshape(-1)
+    idx = np.repeat(np.arange(n * L), flat_reps)
+    res = out.reshape(-1)[idx]
+    second = np.zeros(idx.shape[0], dtype=bool)
+    if idx.shape[0] > 1:
+        second[1:] = idx[1:] == idx[:-1]
+    res[second] = ACGT[rng.integers(0, 4, size=int(second.sum()), dtype=np.uint8)]
+    ss = SeqSet.__new__(SeqSet)
+    ss.lens = reps.sum(axis=1).astype(np.int32)
+    ss.offs = np.zeros(n, dtype=np.int64)
+    np.cumsum(ss.lens[:-1], out=ss.offs[1:])
+    ss.cat = np.empty(res.shape[0] + 1, dtype=np.uint8)
+    ss.cat[:-1] = res
+    ss.cat[-1] = 0
+    return ss
+
+
+def config2_db(n_db: int = 100_000, db_len: int = 1500, seed: int = 2024) -> np.ndarray:
+    """C2 database as an (n_db, db_len) ASCII matrix."""
+    return random_seqs(np.random.default_rng(seed), n_db, db_len)
+
+
+def config2_query_batch(dbm: np.ndarray, n_q: int, q_len: int = 250, div: float = 0.05,
+                        seed: int = 2024, batch: int = 0):
+    """Batch `batch` of the C2 query stream: windows of uniformly chosen DB sequences, mut(., div).
+    Returns (SeqSet, source target per query)."""
+    rng = np.random.default_rng([seed, 7919, batch])
+    n_db, db_len = dbm.shape
+    src = rng.integers(0, n_db, size=n_q)
+    start = rng.integers(0, db_len - q_len + 1, size=n_q)
+    cols = start[:, None] + np.arange(q_len)[None, :]
+    win = dbm[src[:, None], cols]
+    return mutate_batch(rng, win, div), src
