@@ -58,6 +58,21 @@ __device__ __forceinline__ uint32_t max_flag(uint32_t a, uint32_t b, uint32_t & 
   return m;
 }
 
+// shared-memory loads by 32-bit shared-window address: keeps ptxas from re-deriving the generic
+// base address (S2R/S2UR/LEA chains) inside the hot loop
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+
 __device__ __forceinline__ int code_to_2bit(int c4) { return (c4 == 2) ? 1 : (c4 == 4) ? 2 : (c4 == 8) ? 3 : 0; }
 
 // Semantics self-test of the DPX intrinsic the fast kernel leans on (run once per context).
@@ -135,7 +150,14 @@ nw_fast_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
   uint4 * const rA = ringA[wib];
   uint32_t * const rB = ringB[wib];
   uint2 * const mybnd = bnd + tk.bnd_off;
-  uint8_t const * const lutb = reinterpret_cast<uint8_t const *>(lut);
+  uint32_t const lut_s = static_cast<uint32_t>(__cvta_generic_to_shared(lut));
+  uint32_t const rA_s = static_cast<uint32_t>(__cvta_generic_to_shared(rA));
+  uint32_t const rB_s = static_cast<uint32_t>(__cvta_generic_to_shared(rB));
+  {
+    uint32_t a = rA_s, b = rB_s;  // pin the ring addresses in registers (see rowoff below)
+    asm volatile("" : "+r"(a), "+r"(b));
+    const_cast<uint32_t &>(rA_s) = a; const_cast<uint32_t &>(rB_s) = b;
+  }
 
   for (int strip = 0; strip < nstrips; strip++) {
     int const row0 = strip * strip_rows + lane * R;
@@ -145,25 +167,30 @@ nw_fast_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
     for (int r = 0; r < R; r++) {
       int const i = row0 + r;
       int const code = (i < Q) ? (qsym[i] & 15) : 0;
-      rowoff[r] = GENERAL ? static_cast<uint32_t>(code) * 1024u
-                          : (static_cast<uint32_t>(code_to_2bit(code)) * 16u * 32u + lane) * 4u;
+      rowoff[r] = lut_s + (GENERAL ? static_cast<uint32_t>(code) * 1024u
+                                   : (static_cast<uint32_t>(code_to_2bit(code)) * 16u * 32u + lane) * 4u);
       bool const last = (i == Q - 1);
       QRq[r] = pk1(last ? QRqr : QRqi);
       Rq[r] = pk1(last ? Rqr : Rqi);
       Hl[r] = BIAS2 - pk1(gotl + (i + 1) * getl);  // H(i,-1)     (align_simd.cpp:852-853)
       E[r] = Hl[r] - QRq[r];                       // E(i,0)      (align_simd.cpp:855-857)
+      // per-row constants must live in registers: without this ptxas re-derives the "is this the
+      // query's last row" select (compare + select + repack) for every row of every step
+      asm volatile("" : "+r"(rowoff[r]), "+r"(QRq[r]), "+r"(Rq[r]));
     }
     // H(row0-1,-1): the diagonal input of this lane's first row at column 0
     uint32_t diag_in = (row0 == 0) ? BIAS2 : BIAS2 - pk1(gotl + row0 * getl);
     uint32_t Hout = BIAS2, Fout = BIAS2;
     uint8_t * const dstrip = dir + tk.dir_off + static_cast<size_t>(strip) * strip_bytes;
     bool const write_bnd = (strip + 1 < nstrips) && (lane == 31);
+    bool const capture = (strip == klast) && (lane == llast);
 
-    for (int s = 0; s < nsteps; s++) {
-      if ((s & 31) == 0) {
-        // refill the ring with columns [s, s+32): one column per lane, coalesced
+    uint32_t * dptr = reinterpret_cast<uint32_t *>(dstrip) + static_cast<size_t>(lane) * RW;
+    for (int s0 = 0; s0 < nsteps; s0 += 32) {
+      {
+        // refill the ring with columns [s0, s0+32): one column per lane, coalesced
         __syncwarp();
-        int const cc = s + lane;
+        int const cc = s0 + lane;
         if (cc < dmax) {
           int const a = (cc < Dlo) ? (dlo_p[cc] & 15) : 0;
           int const b = (cc < Dhi) ? (dhi_p[cc] & 15) : 0;
@@ -174,68 +201,77 @@ nw_fast_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
           // (align_simd.cpp:1741-1751)
           rec.y = pk2(cc >= Dlo - 1 ? QRtr : QRti, cc >= Dhi - 1 ? QRtr : QRti);
           rec.z = pk2(cc >= Dlo - 1 ? Rtr : Rti, cc >= Dhi - 1 ? Rtr : Rti);
-          uint32_t fin;
+          uint32_t fin0;
           if (strip == 0) {
             rec.w = BIAS2 - pk1(goql + (cc + 1) * geql);  // H(-1,c)  (align_simd.cpp:1895-1901)
-            fin = rec.w - rec.y;                          // F(0,c)   (align_simd.cpp:830-833)
+            fin0 = rec.w - rec.y;                         // F(0,c)   (align_simd.cpp:830-833)
           } else {
             uint2 const v = __ldcg(mybnd + cc);
             rec.w = v.x;
-            fin = v.y;
+            fin0 = v.y;
           }
           rA[cc & (RING - 1)] = rec;
-          rB[cc & (RING - 1)] = fin;
+          rB[cc & (RING - 1)] = fin0;
         }
         __syncwarp();
       }
+      int const kend = min(32, nsteps - s0);
+      int c = s0 - lane;
+      for (int k = 0; k < kend; k++, c++, dptr += 32 * RW) {
+        uint32_t hin = __shfl_up_sync(0xffffffffu, Hout, 1);
+        uint32_t fin = __shfl_up_sync(0xffffffffu, Fout, 1);
+        if (c >= 0 && c < dmax) {
+          uint32_t const slot = static_cast<uint32_t>(c) & (RING - 1);
+          uint4 const rec = lds128(rA_s + slot * 16u);
+          if (lane == 0) { hin = rec.w; fin = lds32(rB_s + slot * 4u); }
 
-      uint32_t hin = __shfl_up_sync(0xffffffffu, Hout, 1);
-      uint32_t fin = __shfl_up_sync(0xffffffffu, Fout, 1);
-      int const c = s - lane;
-      if (c >= 0 && c < dmax) {
-        uint4 const rec = rA[c & (RING - 1)];
-        if (lane == 0) { hin = rec.w; fin = rB[c & (RING - 1)]; }
-
-        uint32_t F = fin;
-        uint32_t diag = diag_in;
-        uint32_t wd[RW];
+          // H(i-1,j-1) + S for every row first: the old column is dead before the new one is
+          // produced (no register rotation at the loop edge) and these adds are off the F chain
+          uint32_t t[R];
 #pragma unroll
-        for (int k = 0; k < RW; k++) { wd[k] = 0; }
+          for (int r = 0; r < R; r++) {
+            uint32_t const S = lds32(rowoff[r] + rec.x);
+            t[r] = __vadd2(r == 0 ? diag_in : Hl[r - 1], S);
+          }
+          uint32_t F = fin;
+          uint32_t wd[RW];
+#pragma unroll
+          for (int kk = 0; kk < RW; kk++) { wd[kk] = 0; }
 
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-          uint32_t const sh = 8u * (r & 3);
-          uint32_t & wr = wd[r >> 2];
-          uint32_t const S = *reinterpret_cast<uint32_t const *>(lutb + rowoff[r] + rec.x);
-          uint32_t const t = __vadd2(diag, S);                         // H(i-1,j-1) + S
-          uint32_t const m1 = max_flag(t, F, wr, 1u << sh, 16u << sh);  // up:   F > h
-          uint32_t const h = max_flag(m1, E[r], wr, 2u << sh, 32u << sh);  // left: E > h
-          diag = Hl[r];
-          Hl[r] = h;
-          uint32_t const hf = h - rec.y;                               // H - QR_t
-          uint32_t const f = F - rec.z;                                // F - R_t
-          F = max_flag(hf, f, wr, 4u << sh, 64u << sh);                // extup:   f > hf
-          uint32_t const he = h - QRq[r];
-          uint32_t const e = E[r] - Rq[r];
-          E[r] = max_flag(he, e, wr, 8u << sh, 128u << sh);            // extleft: e > he
-        }
-        Hout = Hl[R - 1];
-        Fout = F;
-        diag_in = hin;
+          for (int r = 0; r < R; r++) {
+            // the 8 flags of this row-step go to a register of their own (a short dependency chain
+            // per row instead of one 32-deep chain per word, which made ptxas park predicates in
+            // P2R/ISETP pairs); one multiply-add per row merges it into the output word
+            uint32_t fb = 0;
+            uint32_t const m1 = max_flag(t[r], F, fb, 1u, 16u);     // up:   F > h
+            uint32_t const h = max_flag(m1, E[r], fb, 2u, 32u);     // left: E > h
+            Hl[r] = h;
+            uint32_t const hf = h - rec.y;                          // H - QR_t
+            uint32_t const f = F - rec.z;                           // F - R_t
+            F = max_flag(hf, f, fb, 4u, 64u);                       // extup:   f > hf
+            uint32_t const he = h - QRq[r];
+            uint32_t const e = E[r] - Rq[r];
+            E[r] = max_flag(he, e, fb, 8u, 128u);                   // extleft: e > he
+            wd[r >> 2] = fb * (1u << (8u * (r & 3))) + wd[r >> 2];
+          }
+          Hout = Hl[R - 1];
+          Fout = F;
+          diag_in = hin;
 
-        uint32_t * const dp = reinterpret_cast<uint32_t *>(dstrip) + (static_cast<size_t>(s) * 32 + lane) * RW;
-        if (RW == 1) { dp[0] = wd[0]; }
-        else if (RW == 2) { *reinterpret_cast<uint2 *>(dp) = make_uint2(wd[0], wd[1]); }
-        else { *reinterpret_cast<uint4 *>(dp) = make_uint4(wd[0], wd[1], wd[RW > 2 ? 2 : 0], wd[RW > 3 ? 3 : 0]); }
+          if (RW == 1) { dptr[0] = wd[0]; }
+          else if (RW == 2) { *reinterpret_cast<uint2 *>(dptr) = make_uint2(wd[0], wd[1]); }
+          else { *reinterpret_cast<uint4 *>(dptr) = make_uint4(wd[0], wd[1], wd[RW > 2 ? 2 : 0], wd[RW > 3 ? 3 : 0]); }
 
-        if (write_bnd) { __stcg(mybnd + c, make_uint2(Hout, Fout)); }
+          if (write_bnd) { __stcg(mybnd + c, make_uint2(Hout, Fout)); }
 
-        if (strip == klast && lane == llast && (c == Dlo - 1 || c == Dhi - 1)) {
-          uint32_t v = 0;
+          if (capture && (c == Dlo - 1 || c == Dhi - 1)) {
+            uint32_t v = 0;
 #pragma unroll
-          for (int r = 0; r < R; r++) { if (r == rlast) { v = Hl[r]; } }
-          if (c == Dlo - 1) { score_lo = static_cast<int>(v & 0xffffu) - static_cast<int>(BIAS); }
-          if (c == Dhi - 1) { score_hi = static_cast<int>(v >> 16) - static_cast<int>(BIAS); }
+            for (int r = 0; r < R; r++) { if (r == rlast) { v = Hl[r]; } }
+            if (c == Dlo - 1) { score_lo = static_cast<int>(v & 0xffffu) - static_cast<int>(BIAS); }
+            if (c == Dhi - 1) { score_hi = static_cast<int>(v >> 16) - static_cast<int>(BIAS); }
+          }
         }
       }
     }

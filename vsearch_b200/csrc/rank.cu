@@ -28,11 +28,13 @@ namespace vsg {
 
 constexpr int SHARD_BITS = 15;
 constexpr int SHARD = 1 << SHARD_BITS;  // targets per shard
-constexpr int RANK_THREADS = 256;
+constexpr int RANK_THREADS = 512;
 constexpr int KMER_CAP = 2048;          // distinct-k-mer capacity per query (query length <= 2047 + k)
 constexpr int CAND_CAP = 2048;          // candidate keys held in shared memory
 constexpr int TOPHITS_MAX = 1024;
 constexpr int SCAN_SEG_WORDS = 512;     // counters are scanned 1024 at a time (<= 1024 new candidates)
+constexpr uint16_t POST_PAD = 0x8000;   // list padding: counts into a dummy counter word past the shard
+constexpr int COUNTER_WORDS = SHARD / 2 + 1;
 
 struct ShardDev {
   const uint32_t * start;  // 4^k + 1
@@ -100,6 +102,18 @@ __global__ void index_build_kernel(DevSeqs db, int t0, int nt, int k, int mask_l
   }
 }
 
+// lists are padded to a multiple of 8 entries so that every list starts on a 16-byte boundary
+__global__ void pad_counts_kernel(uint32_t * __restrict__ count, int n)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { count[i] = (count[i] + 7u) & ~7u; }
+}
+__global__ void fill_u16_kernel(uint16_t * __restrict__ p, size_t n, uint16_t v)
+{
+  size_t const i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) { p[i] = v; }
+}
+
 // ---- bitonic sort helpers on shared memory (descending for keys, ascending for k-mers) ----------
 template <typename T, bool DESC>
 __device__ void bitonic_sort_shared(T * a, int n /* power of two */)
@@ -142,9 +156,9 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
             int32_t * __restrict__ status)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  uint32_t * const counters = reinterpret_cast<uint32_t *>(smem);                 // SHARD/2 words
-  uint64_t * const cand = reinterpret_cast<uint64_t *>(smem + SHARD * 2);         // CAND_CAP
-  uint32_t * const kmers = reinterpret_cast<uint32_t *>(smem + SHARD * 2 + CAND_CAP * 8);  // KMER_CAP
+  uint64_t * const cand = reinterpret_cast<uint64_t *>(smem);                     // CAND_CAP
+  uint32_t * const counters = reinterpret_cast<uint32_t *>(smem + CAND_CAP * 8);  // COUNTER_WORDS (+pad)
+  uint32_t * const kmers = counters + COUNTER_WORDS + 3;                          // KMER_CAP
   uint32_t * const lbeg = kmers + KMER_CAP;                                       // KMER_CAP
   uint32_t * const llen = lbeg + KMER_CAP;                                        // KMER_CAP
   __shared__ int s_ncand, s_nk;
@@ -191,7 +205,7 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
     for (int sh = 0; sh < nshards; sh++) {
       ShardDev const S = shards[sh];
       // 2. zero the counters; fetch the bounds of every k-mer's posting list in this shard
-      for (int i = threadIdx.x; i < SHARD / 2; i += blockDim.x) { counters[i] = 0; }
+      for (int i = threadIdx.x; i < COUNTER_WORDS; i += blockDim.x) { counters[i] = 0; }
       for (int i = threadIdx.x; i < np2; i += blockDim.x) {
         uint32_t const km = kmers[i];
         uint32_t b = 0, n = 0;
@@ -199,21 +213,52 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
         lbeg[i] = b; llen[i] = n;
       }
       __syncthreads();
-      // 3. postings -> counters, one warp per list (targets within a list are distinct)
-      for (int i = warp; i < np2; i += NWARPS) {
-        uint32_t const n = llen[i];
-        const uint16_t * __restrict__ pl = S.post + lbeg[i];
-        for (uint32_t e = lane; e < n; e += 32) {
-          uint32_t const t = pl[e];
-          atomicAdd(&counters[t >> 1], (t & 1) ? 0x10000u : 1u);
+      // 3. postings -> counters (targets within a list are distinct, lists collide -> shared-memory
+      //    atomics).  Lists are 16-byte aligned and padded, so a lane pulls 8 targets per 128-bit
+      //    load.  A warp walks TWO lists at a time and issues up to three loads per lane and list
+      //    before it touches a counter: six independent HBM requests per lane hide the latency that a
+      //    one-list-at-a-time loop exposes once per list (the typical list is ~70 vectors long).
+      //    Padding entries land in the dummy word counters[SHARD/2].
+      for (int i = warp; i < np2; i += 2 * NWARPS) {
+        int const i2 = i + NWARPS;
+        uint32_t const na = llen[i] >> 3;
+        uint32_t const nb = (i2 < np2) ? (llen[i2] >> 3) : 0u;
+        const uint4 * __restrict__ pa = reinterpret_cast<const uint4 *>(S.post + lbeg[i]);
+        const uint4 * __restrict__ pb = reinterpret_cast<const uint4 *>(S.post + (i2 < np2 ? lbeg[i2] : 0u));
+        uint32_t const nmax = na > nb ? na : nb;
+        for (uint32_t base = 0; base < nmax; base += 96) {
+          uint4 x[6];
+#pragma unroll
+          for (int u = 0; u < 3; u++) {
+            uint32_t const e = base + lane + 32u * u;
+            x[u] = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);
+            x[3 + u] = x[u];
+            if (e < na) { x[u] = __ldg(pa + e); }
+            if (e < nb) { x[3 + u] = __ldg(pb + e); }
+          }
+#pragma unroll
+          for (int u = 0; u < 6; u++) {
+            uint32_t const w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+            if (w[0] == 0x80008000u && w[3] == 0x80008000u) { continue; }  // nothing loaded (lists are short)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              uint32_t const a = w[k] & 0xffffu, b = w[k] >> 16;
+              atomicAdd(&counters[a >> 1], (a & 1) ? 0x10000u : 1u);
+              atomicAdd(&counters[b >> 1], (b & 1) ? 0x10000u : 1u);
+            }
+          }
         }
       }
       __syncthreads();
       // 4. threshold scan in segments; sort-and-cut the candidate list when it could overflow
       int const nwords = (S.nt + 1) >> 1;
       for (int seg = 0; seg < nwords; seg += SCAN_SEG_WORDS) {
-        if (s_ncand + 2 * SCAN_SEG_WORDS > CAND_CAP) {
-          int const m = s_ncand;
+        // every thread must take the same decision: read the fill level, then fence the read off
+        // from the appends of threads that are already past this point
+        int const level = s_ncand;
+        __syncthreads();
+        if (level + 2 * SCAN_SEG_WORDS > CAND_CAP) {
+          int const m = level;
           int const p2 = next_pow2(m);
           for (int i = m + threadIdx.x; i < p2; i += blockDim.x) { cand[i] = 0; }
           bitonic_sort_shared<uint64_t, true>(cand, p2);
@@ -237,8 +282,43 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
         __syncthreads();
       }
     }
-    // 5. final order
-    int const m = s_ncand;
+    // 5. final order.  Usually far more targets pass the k-mer threshold than are wanted: find the
+    //    count T of the tophits-th best with a histogram, keep count >= T, sort only those.
+    int m = s_ncand;
+    __syncthreads();
+    if (m > 2 * tophits) {
+      uint32_t * const hist = lbeg;  // 2 * KMER_CAP words available, counts are <= nk <= KMER_CAP
+      int const nb = nk + 1;
+      for (int i = threadIdx.x; i < nb; i += blockDim.x) { hist[i] = 0; }
+      __syncthreads();
+      for (int i = threadIdx.x; i < m; i += blockDim.x) { atomicAdd(&hist[static_cast<uint32_t>(cand[i] >> 49)], 1u); }
+      __syncthreads();
+      if (warp == 0) {
+        int acc = 0, T = 0;
+        for (int top = nb - 1; top >= 0; top -= 32) {
+          int const b = top - lane;
+          int v = b >= 0 ? static_cast<int>(hist[b]) : 0;
+          // inclusive prefix over lanes = suffix over bins (lane 0 is the highest bin)
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) { int const o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) { v += o; } }
+          unsigned const hit = __ballot_sync(0xffffffffu, acc + v >= tophits);
+          if (hit != 0u) { T = top - (__ffs(hit) - 1); break; }
+          acc += __shfl_sync(0xffffffffu, v, 31);
+        }
+        if (lane == 0) { s_nk = T; s_ncand = 0; }
+      }
+      __syncthreads();
+      uint64_t const tkey = static_cast<uint64_t>(static_cast<uint32_t>(s_nk)) << 49;
+      // compact in place: read everything first, then write the survivors
+      uint64_t mine[CAND_CAP / RANK_THREADS];
+      int cnt = 0;
+      for (int i = threadIdx.x; i < m; i += blockDim.x) { uint64_t const kx = cand[i]; if (kx >= tkey) { mine[cnt++] = kx; } }
+      __syncthreads();
+      int base = cnt > 0 ? atomicAdd(&s_ncand, cnt) : 0;
+      for (int i = 0; i < cnt; i++) { cand[base + i] = mine[i]; }
+      __syncthreads();
+      m = s_ncand;
+    }
     int const p2 = next_pow2(m > 1 ? m : 1);
     for (int i = m + threadIdx.x; i < p2; i += blockDim.x) { cand[i] = 0; }
     bitonic_sort_shared<uint64_t, true>(cand, p2);
@@ -253,7 +333,7 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
   }
 }
 
-constexpr size_t RANK_SMEM = SHARD * 2 + CAND_CAP * 8 + KMER_CAP * 4 * 3;
+constexpr size_t RANK_SMEM = CAND_CAP * 8 + (COUNTER_WORDS + 3) * 4 + KMER_CAP * 4 * 3;
 
 }  // namespace vsg
 
@@ -307,6 +387,8 @@ extern "C" int vsg_index_create(vsg_ctx * c, const vsg_seqset * db, int wordleng
     index_build_kernel<false><<<nt, 128, bitmap_bytes, c->stream>>>(db->d, t0, nt, k, mask_lower,
                                                                     static_cast<uint32_t *>(cnt.p), nullptr, nullptr);
     count_launch();
+    pad_counts_kernel<<<static_cast<unsigned>((hashsize + 255) / 256), 256, 0, c->stream>>>(static_cast<uint32_t *>(cnt.p), static_cast<int>(hashsize));
+    count_launch();
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, static_cast<uint32_t *>(cnt.p), static_cast<uint32_t *>(bs.p),
                                   static_cast<int>(hashsize + 1), c->stream);
@@ -320,6 +402,11 @@ extern "C" int vsg_index_create(vsg_ctx * c, const vsg_seqset * db, int wordleng
     DevBuf & bp = ix->b_post[static_cast<size_t>(sh)];
     if ((rc = bp.reserve(sizeof(uint16_t) * (static_cast<size_t>(total) + 64))) != VSG_OK) { vsg_index_destroy(ix); return rc; }
     VSG_CUDA_OK(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * (hashsize + 1), c->stream));
+    if (total > 0) {
+      fill_u16_kernel<<<static_cast<unsigned>((static_cast<size_t>(total) + 255) / 256), 256, 0, c->stream>>>(
+          static_cast<uint16_t *>(bp.p), static_cast<size_t>(total), POST_PAD);
+      count_launch();
+    }
     index_build_kernel<true><<<nt, 128, bitmap_bytes, c->stream>>>(db->d, t0, nt, k, mask_lower,
                                                                    static_cast<uint32_t *>(cnt.p),
                                                                    static_cast<uint32_t *>(bs.p),

@@ -13,8 +13,11 @@
 #include "vsg_internal.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace vsg {
 int rank_enqueue(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * queries, int64_t q0, int64_t nq,
@@ -140,7 +143,26 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   int const tophits = static_cast<int>(tophits64);
   int const nstrands = opts->strand_both ? 2 : 1;
 
-  int64_t const BATCH = 32768;
+  // Sub-batches run on a few host threads, each with its own child context (stream + scratch):
+  // while one thread replays accept/reject decisions or builds task lists, the kernels of the
+  // others keep the GPU busy.  Results land in disjoint slots, so no ordering is needed.
+  int64_t const BATCH = 16384;
+  int64_t const nbatches = (nq + BATCH - 1) / BATCH;
+  int nthreads = 4;
+  if (const char * e = std::getenv("VSG_HOST_THREADS")) { nthreads = std::max(1, std::atoi(e)); }
+  nthreads = static_cast<int>(std::min<int64_t>(nthreads, nbatches));
+  while (static_cast<int>(c->children.size()) < nthreads) {
+    vsg_ctx * ch = nullptr;
+    int const r = vsg_ctx_create(c->device, &c->scoring, &ch);
+    if (r != VSG_OK) { return r; }
+    c->children.push_back(ch);
+  }
+  for (int t = 0; t < nthreads; t++) {
+    c->children[static_cast<size_t>(t)]->dir_budget = std::max<size_t>(c->dir_budget / static_cast<size_t>(nthreads), static_cast<size_t>(1) << 30);
+    c->children[static_cast<size_t>(t)]->fast_disabled = c->fast_disabled;
+  }
+
+  auto run_batch = [&](vsg_ctx * c, int64_t b0, int64_t & total_pairs, int64_t & total_cells) -> int {
   std::vector<uint32_t> h_seqno, h_count;
   std::vector<int32_t> h_n;
   std::vector<QState> st;
@@ -151,8 +173,9 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   std::vector<uint16_t> a_al, a_ma, a_mi, a_ga;
   std::vector<int32_t> a_tr;
   std::vector<Hit> joined;
+  VSG_CUDA_OK(cudaSetDevice(c->device));
+  {
 
-  for (int64_t b0 = 0; b0 < nq; b0 += BATCH) {
     int64_t const bn = std::min(BATCH, nq - b0);
     vsg_seqset * rc_set = nullptr;
     if (nstrands == 2) {
@@ -322,6 +345,40 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
       counts[b0 + q] = n;
     }
     if (rc_set) { vsg_seqset_destroy(rc_set); }
+  }
+  return VSG_OK;
+  };
+
+  std::atomic<int64_t> next{0};
+  std::vector<int> rcs(static_cast<size_t>(nthreads), VSG_OK);
+  std::vector<std::string> msgs(static_cast<size_t>(nthreads));
+  std::vector<int64_t> tp(static_cast<size_t>(nthreads), 0), tc(static_cast<size_t>(nthreads), 0);
+  auto worker = [&](int t) {
+    vsg_ctx * wc = c->children[static_cast<size_t>(t)];
+    for (;;) {
+      int64_t const bi = next.fetch_add(1);
+      if (bi >= nbatches) { break; }
+      int const r = run_batch(wc, bi * BATCH, tp[static_cast<size_t>(t)], tc[static_cast<size_t>(t)]);
+      if (r != VSG_OK) { rcs[static_cast<size_t>(t)] = r; msgs[static_cast<size_t>(t)] = vsg_last_error(); next.store(nbatches); break; }
+    }
+  };
+  if (nthreads == 1) {
+    worker(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; t++) { pool.emplace_back(worker, t); }
+    for (auto & th : pool) { th.join(); }
+  }
+  for (int t = 0; t < nthreads; t++) {
+    vsg_ctx * wc = c->children[static_cast<size_t>(t)];
+    c->prof_cells += wc->prof_cells; c->prof_fast += wc->prof_fast; c->prof_exact += wc->prof_exact;
+    c->prof_fwd_launches += wc->prof_fwd_launches;
+    c->prof_fwd_ms += wc->prof_fwd_ms; c->prof_tb_ms += wc->prof_tb_ms; c->prof_rank_ms += wc->prof_rank_ms;
+    vsg_profile_reset(wc);
+    total_pairs += tp[static_cast<size_t>(t)]; total_cells += tc[static_cast<size_t>(t)];
+  }
+  for (int t = 0; t < nthreads; t++) {
+    if (rcs[static_cast<size_t>(t)] != VSG_OK) { Error::set(msgs[static_cast<size_t>(t)]); return rcs[static_cast<size_t>(t)]; }
   }
   if (work != nullptr) { work[0] = total_pairs; work[1] = total_cells; }
   return VSG_OK;

@@ -184,6 +184,8 @@ extern "C" int vsg_ctx_create(int device, const vsg_scoring * scoring, vsg_ctx *
 extern "C" void vsg_ctx_destroy(vsg_ctx * c)
 {
   if (c == nullptr) { return; }
+  for (vsg_ctx * ch : c->children) { vsg_ctx_destroy(ch); }
+  c->children.clear();
   cudaSetDevice(c->device);
   if (c->stream != nullptr) { cudaStreamSynchronize(c->stream); }
   for (DevBuf * b : {&c->dir, &c->bnd, &c->he, &c->cigar_scratch, &c->cigar_dense, &c->stats,
@@ -407,7 +409,8 @@ int run_chunk(vsg_ctx * c, const vsg_seqset * qs, const vsg_seqset * ts, Chunk &
   for (auto & g : ch.fast) {
     for (auto & v : g) {
       // longest first: the tail of the grid is made of the short ones
-      std::sort(v.begin(), v.end(), [](const FastTask & a, const FastTask & b) { return a.dmax > b.dmax; });
+      auto const longer = [](const FastTask & a, const FastTask & b) { return a.dmax > b.dmax; };
+      if (!std::is_sorted(v.begin(), v.end(), longer)) { std::sort(v.begin(), v.end(), longer); }
       if (!v.empty()) { std::memcpy(h_fast + pos, v.data(), sizeof(FastTask) * v.size()); }
       pos += v.size();
     }

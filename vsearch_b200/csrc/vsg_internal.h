@@ -118,10 +118,11 @@ struct vsg_ctx {
   vsg::DevBuf dir, bnd, he, cigar_scratch, cigar_dense, stats, tasks_fast, tasks_exact, pairs,
       cigar_len, cigar_offs, cub_tmp, rank_tmp;
   vsg::PinBuf h_tasks, h_stats, h_pairs, h_misc;
-  size_t dir_budget = (size_t)24 << 30;
+  size_t dir_budget = (size_t)64 << 30;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // cumulative profile since the last vsg_profile_reset (kernel times from cudaEvents on `stream`)
   int64_t prof_cells = 0, prof_fast = 0, prof_exact = 0, prof_fwd_launches = 0;
   float prof_fwd_ms = 0.f, prof_tb_ms = 0.f, prof_rank_ms = 0.f;
   bool rank_pending = false;
+  std::vector<vsg_ctx *> children;  // per-host-thread contexts of vsg_search_batch
 };
