@@ -439,14 +439,10 @@ struct CigarWriter {
 };
 
 template <bool TEXT>
-__global__ void traceback_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
-                                 const PairDesc * __restrict__ pairs, int npairs,
-                                 uint8_t const * __restrict__ dir, char * __restrict__ cigar_scratch,
-                                 int32_t * __restrict__ stats)
+__device__ __forceinline__ void traceback_one(const ScoreParams & sp, const DevSeqs & qs, const DevSeqs & ts,
+                                              const PairDesc & pd, uint8_t const * __restrict__ dir,
+                                              char * __restrict__ cigar_scratch, int32_t * __restrict__ stats)
 {
-  int const p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= npairs) { return; }
-  PairDesc const pd = pairs[p];
   int32_t * const st = stats + static_cast<size_t>(pd.out) * VSG_STAT_WORDS;
   if (st[VSG_STAT_SCORE] == VSG_SCORE_SENTINEL) {
     st[VSG_STAT_ALIGNED] = 0; st[VSG_STAT_MATCHES] = 0; st[VSG_STAT_MISMATCHES] = 0;
@@ -535,6 +531,49 @@ __global__ void traceback_kernel(const __grid_constant__ ScoreParams sp, DevSeqs
   st[VSG_STAT_TRIM_RIGHT] = last_run_op == 'D' ? last_run : (last_run_op == 'I' ? -last_run : 0);
   st[VSG_STAT_CIGARLEN] = cw.len;
   // the text (if any) sits right-aligned: it ends with its NUL at region + Q + D
+}
+
+template <bool TEXT>
+__global__ void traceback_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
+                                 const PairDesc * __restrict__ pairs, int npairs,
+                                 uint8_t const * __restrict__ dir, char * __restrict__ cigar_scratch,
+                                 int32_t * __restrict__ stats)
+{
+  int const p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) { return; }
+  PairDesc const pd = pairs[p];
+  traceback_one<TEXT>(sp, qs, ts, pd, dir, cigar_scratch, stats);
+}
+
+// statistics-only traceback straight from the forward tasks (no per-pair descriptors to build,
+// upload or read): thread 2k / 2k+1 = first / second target of task k
+__global__ void traceback_fast_tasks_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
+                                            const FastTask * __restrict__ tasks, int ntasks, int R,
+                                            uint8_t const * __restrict__ dir, int32_t * __restrict__ stats)
+{
+  int const id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= 2 * ntasks) { return; }
+  FastTask const tk = tasks[id >> 1];
+  int const half = id & 1;
+  int const out = half ? tk.out_hi : tk.out_lo;
+  if (out < 0) { return; }
+  PairDesc pd;
+  pd.q = tk.q; pd.t = half ? tk.thi : tk.tlo; pd.dir_off = tk.dir_off; pd.kind = 0; pd.out = out;
+  pd.R = R; pd.half = half; pd.dmax = tk.dmax; pd.cigar_off = 0;
+  traceback_one<false>(sp, qs, ts, pd, dir, nullptr, stats);
+}
+
+__global__ void traceback_exact_tasks_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
+                                             const ExactTask * __restrict__ tasks, int ntasks,
+                                             uint8_t const * __restrict__ dir, int32_t * __restrict__ stats)
+{
+  int const id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= ntasks) { return; }
+  ExactTask const tk = tasks[id];
+  PairDesc pd;
+  pd.q = tk.q; pd.t = tk.t; pd.dir_off = tk.dir_off; pd.kind = 1; pd.out = tk.out;
+  pd.R = 1; pd.half = 0; pd.dmax = 0; pd.cigar_off = 0;
+  traceback_one<false>(sp, qs, ts, pd, dir, nullptr, stats);
 }
 
 // CIGAR texts sit right-aligned in their scratch regions; pack them densely (NUL-terminated)

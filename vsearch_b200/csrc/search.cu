@@ -18,6 +18,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <chrono>
+#include <cstdio>
 
 namespace vsg {
 int rank_enqueue(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * queries, int64_t q0, int64_t nq,
@@ -37,16 +39,16 @@ constexpr int MAXDELAYED = 8;  // searchcore.hpp:71
 // searchcore.hpp:75-76
 constexpr int minwordmatches_defaults[16] = {-1, -1, -1, 18, 17, 16, 15, 14, 12, 11, 10, 9, 8, 7, 5, 3};
 
-struct Hit {  // the fields of struct hit (searchcore.hpp:78-126) this path needs
-  int target = 0, strand = 0;
-  unsigned count = 0;
-  bool accepted = false, rejected = false, aligned = false, weak = false;
-  int nwscore = 0, nwdiff = 0, nwgaps = 0, nwindels = 0, nwalignmentlength = 0;
-  int matches = 0, mismatches = 0;
-  int internal_alignmentlength = 0, internal_gaps = 0, internal_indels = 0;
-  int trim_q_left = 0, trim_q_right = 0, trim_t_left = 0, trim_t_right = 0;
-  double id = 0, id0 = 0, id1 = 0, id2 = 0, id3 = 0, id4 = 0;
-  int shortest = 0, longest = 0;
+struct Hit {  // the fields of struct hit (searchcore.hpp:78-126) this path needs; POD, zeroed on use
+  int target, strand;
+  unsigned count;
+  bool accepted, rejected, aligned, weak;
+  int nwscore, nwdiff, nwgaps, nwindels, nwalignmentlength;
+  int matches, mismatches;
+  int internal_alignmentlength, internal_gaps, internal_indels;
+  int trim_q_left, trim_q_right, trim_t_left, trim_t_right;
+  double id, id0, id1, id2, id3, id4;
+  int shortest, longest;
 };
 
 struct QState {
@@ -146,9 +148,10 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   // Sub-batches run on a few host threads, each with its own child context (stream + scratch):
   // while one thread replays accept/reject decisions or builds task lists, the kernels of the
   // others keep the GPU busy.  Results land in disjoint slots, so no ordering is needed.
-  int64_t const BATCH = 16384;
+  int64_t BATCH = 4096;
+  if (const char * e = std::getenv("VSG_SUBBATCH")) { BATCH = std::max<int64_t>(256, std::atoll(e)); }
   int64_t const nbatches = (nq + BATCH - 1) / BATCH;
-  int nthreads = 4;
+  int nthreads = 8;
   if (const char * e = std::getenv("VSG_HOST_THREADS")) { nthreads = std::max(1, std::atoi(e)); }
   nthreads = static_cast<int>(std::min<int64_t>(nthreads, nbatches));
   while (static_cast<int>(c->children.size()) < nthreads) {
@@ -166,7 +169,8 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   std::vector<uint32_t> h_seqno, h_count;
   std::vector<int32_t> h_n;
   std::vector<QState> st;
-  std::vector<Hit> hits;
+  Hit * hits = nullptr;  // bn*nstrands*tophits slots, deliberately uninitialised (each is zeroed when popped)
+  struct HitFree { Hit ** p; ~HitFree() { std::free(*p); } } hit_free{&hits};
   std::vector<uint32_t> pq, pt;
   std::vector<int> pstate;  // which state each pair belongs to
   std::vector<int16_t> a_score;
@@ -174,6 +178,13 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   std::vector<int32_t> a_tr;
   std::vector<Hit> joined;
   VSG_CUDA_OK(cudaSetDevice(c->device));
+  static const bool trace = std::getenv("VSG_TRACE") != nullptr;
+  auto now = []() { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  double t_rank = 0, t_init = 0, t_gather = 0, t_align = 0, t_replay = 0, t_join = 0;
+  auto tp0 = now();
   {
 
     int64_t const bn = std::min(BATCH, nq - b0);
@@ -204,9 +215,12 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
       }
     }
 
+    t_rank += ms(tp0, now()); tp0 = now();
     // one state per (query, strand); hits preallocated at tophits per state
     st.assign(static_cast<size_t>(bn) * nstrands, QState());
-    hits.assign(static_cast<size_t>(bn) * nstrands * tophits, Hit());
+    std::free(hits);
+    hits = static_cast<Hit *>(std::malloc(sizeof(Hit) * static_cast<size_t>(bn) * nstrands * tophits));
+    if (hits == nullptr) { Error::set("out of host memory"); return VSG_ENOMEM; }
     for (int s = 0; s < nstrands; s++) {
       for (int64_t q = 0; q < bn; q++) {
         QState & S = st[static_cast<size_t>(s) * bn + q];
@@ -217,8 +231,10 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
       }
     }
 
+    t_init += ms(tp0, now());
     bool any = true;
     while (any) {
+      tp0 = now();
       any = false;
       pq.clear(); pt.clear(); pstate.clear();
       // gather: run each active query's candidate loop up to its next align_delayed (searchcore.cpp:915-954)
@@ -229,7 +245,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
         while ((S.finalized + S.delayed < maxaccepts + maxrejects - 1) && (S.rejects < maxrejects) &&
                (S.accepts < maxaccepts) && (S.next < S.ncand)) {
           Hit & h = hits[static_cast<size_t>(S.hit_base) + S.hit_count];
-          h = Hit();
+          std::memset(&h, 0, sizeof(Hit));
           h.target = static_cast<int>(S.cs[S.next]); h.count = S.cc[S.next];
           h.strand = static_cast<int>(si / static_cast<size_t>(bn));
           S.next++;
@@ -254,6 +270,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
       }
       if (!any) { break; }
       size_t const np = pq.size();
+      t_gather += ms(tp0, now()); tp0 = now();
       a_score.resize(np); a_al.resize(np); a_ma.resize(np); a_mi.resize(np); a_ga.resize(np); a_tr.resize(np * 4);
       // pairs of the plus strand index `queries`, those of the minus strand index rc_set: two calls
       size_t split = np;
@@ -272,6 +289,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
         if (r != VSG_OK) { if (rc_set) { vsg_seqset_destroy(rc_set); } return r; }
       }
       total_pairs += static_cast<int64_t>(np);
+      t_align += ms(tp0, now()); tp0 = now();
       // replay: the second half of align_delayed (searchcore.cpp:780-880)
       size_t pi = 0;
       for (size_t si = 0; si < st.size(); si++) {
@@ -319,8 +337,10 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
         S.finalized = S.hit_count;
         S.delayed = 0;
       }
+      t_replay += ms(tp0, now());
     }
 
+    tp0 = now();
     // search_joinhits + result records (search.cpp:466-488)
     for (int64_t q = 0; q < bn; q++) {
       joined.clear();
@@ -345,6 +365,11 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
       counts[b0 + q] = n;
     }
     if (rc_set) { vsg_seqset_destroy(rc_set); }
+    t_join += ms(tp0, now());
+  }
+  if (trace) {
+    std::fprintf(stderr, "[vsg trace] batch@%lld: rank %.1f init %.1f gather %.1f align %.1f replay %.1f join %.1f ms\n",
+                 static_cast<long long>(b0), t_rank, t_init, t_gather, t_align, t_replay, t_join);
   }
   return VSG_OK;
   };

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <chrono>
 
 namespace vsg {
 
@@ -108,24 +109,28 @@ static inline void fast_shape(int Q, bool general, int & R, int & nstrips)
 //     >= -(G + Qpad*Rm) - G - (D+4)*Rm            (left column, then one gap along the row)
 //     <= Smax * min(Qpad, D+4)
 //   E, F and the temporaries (h-QR, e-R, diag+S) stay within 2G+|Smin| below / Smax above that.
-static bool fast_path_ok(const ScoreParams & sp, int Qpad, int D)
+struct FastBound { bool valid; int64_t G, Rm, smax, smin; };
+static FastBound fast_bound_of(const ScoreParams & sp)
 {
-  int G = 0, Rm = 0;
+  FastBound fb{true, 0, 0, 0, 0};
   for (int k = 0; k < 6; k++) {
-    if (sp.go[k] < 0 || sp.ge[k] < 0) { return false; }
-    G = std::max(G, sp.go[k] + sp.ge[k]);
-    Rm = std::max<int>(Rm, sp.ge[k]);
+    if (sp.go[k] < 0 || sp.ge[k] < 0) { fb.valid = false; }
+    fb.G = std::max<int64_t>(fb.G, sp.go[k] + sp.ge[k]);
+    fb.Rm = std::max<int64_t>(fb.Rm, sp.ge[k]);
   }
-  int64_t smax = 0, smin = 0;
   for (int i = 0; i < 16; i++) {
     for (int j = 0; j < 16; j++) {
-      smax = std::max<int64_t>(smax, sp.S[i][j]);
-      smin = std::min<int64_t>(smin, sp.S[i][j]);
+      fb.smax = std::max<int64_t>(fb.smax, sp.S[i][j]);
+      fb.smin = std::min<int64_t>(fb.smin, sp.S[i][j]);
     }
   }
-  int64_t const lb = -(static_cast<int64_t>(G) + static_cast<int64_t>(Qpad) * Rm) - G -
-                     static_cast<int64_t>(D + 4) * Rm - 2LL * G + smin;
-  int64_t const ub = smax * std::min<int64_t>(Qpad, D + 4) + smax;
+  return fb;
+}
+static inline bool fast_path_ok(const FastBound & fb, int Qpad, int D)
+{
+  if (!fb.valid) { return false; }
+  int64_t const lb = -(fb.G + static_cast<int64_t>(Qpad) * fb.Rm) - fb.G - static_cast<int64_t>(D + 4) * fb.Rm - 2 * fb.G + fb.smin;
+  int64_t const ub = fb.smax * std::min<int64_t>(Qpad, D + 4) + fb.smax;
   return lb > -16000 && ub < 16000;
 }
 
@@ -193,6 +198,7 @@ extern "C" void vsg_ctx_destroy(vsg_ctx * c)
                      &c->cub_tmp, &c->rank_tmp}) { b->release(); }
   for (PinBuf * b : {&c->h_tasks, &c->h_stats, &c->h_pairs, &c->h_misc}) { b->release(); }
   for (auto & ev : c->ev) { if (ev != nullptr) { cudaEventDestroy(ev); } }
+  for (auto & ev : c->ev_pool) { cudaEventDestroy(ev); }
   if (c->stream != nullptr) { cudaStreamDestroy(c->stream); }
   delete c;
 }
@@ -363,174 +369,26 @@ void launch_fast(vsg_ctx * c, int R, bool general, const DevSeqs & qs, const Dev
   }
 }
 
-struct HostPair {  // one aligned pair of the current chunk
-  PairDesc pd;
-};
-
-struct Chunk {
-  std::vector<FastTask> fast[2][FAST_RMAX + 1];  // [general][R]
-  std::vector<ExactTask> exact;
-  std::vector<PairDesc> pairs;
+// A chunk = the tasks whose direction blocks share the scratch buffer at the same time.
+struct ClassRun { int R; bool general; size_t first; int count; };  // a run of one kernel class in all_fast
+struct ChunkPlan {
+  std::vector<ClassRun> runs;
+  size_t exact_first = 0; int exact_count = 0;
+  size_t pair_first = 0; int pair_count = 0;  // descriptors (CIGAR mode only)
   uint64_t dir_bytes = 0, bnd_elems = 0, he_elems = 0, cigar_bytes = 0;
   int64_t cells = 0, nfast = 0, nexact = 0;
-  void clear()
-  {
-    for (auto & g : fast) { for (auto & v : g) { v.clear(); } }
-    exact.clear(); pairs.clear();
-    dir_bytes = bnd_elems = he_elems = cigar_bytes = 0;
-    cells = nfast = nexact = 0;
-  }
-  bool empty() const { return pairs.empty(); }
+};
+
+struct ChunkBuilder {  // the chunk being filled
+  std::vector<FastTask> fast[2][FAST_RMAX + 1];
+  std::vector<ExactTask> exact;
+  uint64_t dir_bytes = 0, bnd_elems = 0, he_elems = 0, cigar_bytes = 0;
+  int64_t cells = 0, nfast = 0, nexact = 0;
+  int npairdesc = 0;
+  bool empty() const { return nfast == 0 && nexact == 0; }
 };
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
-
-// enqueue forward + traceback (+ CIGAR packing) for one chunk and bring its results home
-int run_chunk(vsg_ctx * c, const vsg_seqset * qs, const vsg_seqset * ts, Chunk & ch, bool want_cigar,
-              int32_t * h_stats_all, std::vector<std::string> * cigars_out /* per pair slot */)
-{
-  int rc;
-  if ((rc = c->dir.reserve(ch.dir_bytes + 256)) != VSG_OK) { return rc; }
-  if ((rc = c->bnd.reserve(sizeof(uint2) * (ch.bnd_elems + 1))) != VSG_OK) { return rc; }
-  if ((rc = c->he.reserve(sizeof(int16_t) * (ch.he_elems + 1))) != VSG_OK) { return rc; }
-
-  // tasks: all fast classes back to back, then exact
-  size_t nfast_tasks = 0;
-  for (auto & g : ch.fast) { for (auto & v : g) { nfast_tasks += v.size(); } }
-  if ((rc = c->tasks_fast.reserve(sizeof(FastTask) * (nfast_tasks + 1))) != VSG_OK) { return rc; }
-  if ((rc = c->tasks_exact.reserve(sizeof(ExactTask) * (ch.exact.size() + 1))) != VSG_OK) { return rc; }
-  if ((rc = c->pairs.reserve(sizeof(PairDesc) * (ch.pairs.size() + 1))) != VSG_OK) { return rc; }
-  size_t const host_bytes = sizeof(FastTask) * nfast_tasks + sizeof(ExactTask) * ch.exact.size() +
-                            sizeof(PairDesc) * ch.pairs.size() + 64;
-  if ((rc = c->h_tasks.reserve(host_bytes)) != VSG_OK) { return rc; }
-  char * hp = static_cast<char *>(c->h_tasks.p);
-  FastTask * h_fast = reinterpret_cast<FastTask *>(hp);
-  size_t pos = 0;
-  for (auto & g : ch.fast) {
-    for (auto & v : g) {
-      // longest first: the tail of the grid is made of the short ones
-      auto const longer = [](const FastTask & a, const FastTask & b) { return a.dmax > b.dmax; };
-      if (!std::is_sorted(v.begin(), v.end(), longer)) { std::sort(v.begin(), v.end(), longer); }
-      if (!v.empty()) { std::memcpy(h_fast + pos, v.data(), sizeof(FastTask) * v.size()); }
-      pos += v.size();
-    }
-  }
-  ExactTask * h_exact = reinterpret_cast<ExactTask *>(hp + sizeof(FastTask) * nfast_tasks);
-  if (!ch.exact.empty()) { std::memcpy(h_exact, ch.exact.data(), sizeof(ExactTask) * ch.exact.size()); }
-  PairDesc * h_pairs = reinterpret_cast<PairDesc *>(hp + sizeof(FastTask) * nfast_tasks + sizeof(ExactTask) * ch.exact.size());
-  std::memcpy(h_pairs, ch.pairs.data(), sizeof(PairDesc) * ch.pairs.size());
-
-  if (nfast_tasks > 0) {
-    VSG_CUDA_OK(cudaMemcpyAsync(c->tasks_fast.p, h_fast, sizeof(FastTask) * nfast_tasks, cudaMemcpyHostToDevice, c->stream));
-  }
-  if (!ch.exact.empty()) {
-    VSG_CUDA_OK(cudaMemcpyAsync(c->tasks_exact.p, h_exact, sizeof(ExactTask) * ch.exact.size(), cudaMemcpyHostToDevice, c->stream));
-  }
-  VSG_CUDA_OK(cudaMemcpyAsync(c->pairs.p, h_pairs, sizeof(PairDesc) * ch.pairs.size(), cudaMemcpyHostToDevice, c->stream));
-
-  VSG_CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
-  pos = 0;
-  for (int g = 0; g < 2; g++) {
-    for (int R = 1; R <= FAST_RMAX; R++) {
-      auto & v = ch.fast[g][R];
-      if (v.empty()) { continue; }
-      launch_fast(c, R, g != 0, qs->d, ts->d, static_cast<FastTask *>(c->tasks_fast.p) + pos, static_cast<int>(v.size()));
-      pos += v.size();
-    }
-  }
-  if (!ch.exact.empty()) {
-    int const n = static_cast<int>(ch.exact.size());
-    nw_exact_kernel<<<(n + 63) / 64, 64, 0, c->stream>>>(c->sp, qs->d, ts->d, static_cast<ExactTask *>(c->tasks_exact.p), n,
-                                                          static_cast<uint8_t *>(c->dir.p), static_cast<int16_t *>(c->he.p),
-                                                          static_cast<int32_t *>(c->stats.p));
-    count_launch();
-  }
-  VSG_CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
-
-  int const np = static_cast<int>(ch.pairs.size());
-  if (want_cigar) {
-    if ((rc = c->cigar_scratch.reserve(ch.cigar_bytes + 64)) != VSG_OK) { return rc; }
-    traceback_kernel<true><<<(np + 127) / 128, 128, 0, c->stream>>>(
-        c->sp, qs->d, ts->d, static_cast<PairDesc *>(c->pairs.p), np, static_cast<uint8_t *>(c->dir.p),
-        static_cast<char *>(c->cigar_scratch.p), static_cast<int32_t *>(c->stats.p));
-  } else {
-    traceback_kernel<false><<<(np + 127) / 128, 128, 0, c->stream>>>(
-        c->sp, qs->d, ts->d, static_cast<PairDesc *>(c->pairs.p), np, static_cast<uint8_t *>(c->dir.p),
-        nullptr, static_cast<int32_t *>(c->stats.p));
-  }
-  count_launch();
-  VSG_CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
-
-  std::vector<int64_t> h_offs;
-  if (want_cigar) {
-    if ((rc = c->cigar_len.reserve(sizeof(int64_t) * (np + 1))) != VSG_OK) { return rc; }
-    if ((rc = c->cigar_offs.reserve(sizeof(int64_t) * (np + 1))) != VSG_OK) { return rc; }
-    cigar_len_kernel<<<(np + 255) / 256, 256, 0, c->stream>>>(static_cast<PairDesc *>(c->pairs.p),
-                                                               static_cast<int32_t *>(c->stats.p), np,
-                                                               static_cast<int64_t *>(c->cigar_len.p));
-    count_launch();
-    size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, static_cast<int64_t *>(c->cigar_len.p),
-                                  static_cast<int64_t *>(c->cigar_offs.p), np, c->stream);
-    if ((rc = c->cub_tmp.reserve(tmp_bytes + 16)) != VSG_OK) { return rc; }
-    cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, static_cast<int64_t *>(c->cigar_len.p),
-                                  static_cast<int64_t *>(c->cigar_offs.p), np, c->stream);
-    count_launch();
-    // dense size <= scratch size
-    if ((rc = c->cigar_dense.reserve(ch.cigar_bytes + 64)) != VSG_OK) { return rc; }
-    cigar_gather_kernel<<<np, 64, 0, c->stream>>>(static_cast<PairDesc *>(c->pairs.p), np, qs->d, ts->d,
-                                                   static_cast<int32_t *>(c->stats.p),
-                                                   static_cast<int64_t *>(c->cigar_offs.p),
-                                                   static_cast<char *>(c->cigar_scratch.p),
-                                                   static_cast<char *>(c->cigar_dense.p));
-    count_launch();
-    h_offs.resize(static_cast<size_t>(np));
-    VSG_CUDA_OK(cudaMemcpyAsync(h_offs.data(), c->cigar_offs.p, sizeof(int64_t) * np, cudaMemcpyDeviceToHost, c->stream));
-  }
-  VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
-  VSG_CUDA_OK(cudaGetLastError());
-
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->prof_fwd_ms += ms;
-  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->prof_tb_ms += ms;
-  c->prof_cells += ch.cells; c->prof_fast += ch.nfast; c->prof_exact += ch.nexact;
-  for (auto & g : ch.fast) { for (auto & v : g) { c->prof_fwd_launches += v.empty() ? 0 : 1; } }
-  c->prof_fwd_launches += ch.exact.empty() ? 0 : 1;
-
-  // stats of this chunk's pairs: they are scattered over the slot array; copy the covering range
-  int lo = INT32_MAX, hi = -1;
-  for (auto const & pd : ch.pairs) { lo = std::min(lo, pd.out); hi = std::max(hi, pd.out); }
-  if (hi >= lo) {
-    size_t const words = static_cast<size_t>(hi - lo + 1) * VSG_STAT_WORDS;
-    if ((rc = c->h_stats.reserve(words * sizeof(int32_t))) != VSG_OK) { return rc; }
-    VSG_CUDA_OK(cudaMemcpyAsync(c->h_stats.p, static_cast<int32_t *>(c->stats.p) + static_cast<size_t>(lo) * VSG_STAT_WORDS,
-                                words * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    std::vector<char> dense;
-    if (want_cigar) {
-      // total text bytes = offs[np-1] + len[np-1]; fetch the whole used prefix
-      VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
-    }
-    VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
-    int32_t const * hs = static_cast<int32_t *>(c->h_stats.p);
-    for (auto const & pd : ch.pairs) {
-      std::memcpy(h_stats_all + static_cast<size_t>(pd.out) * VSG_STAT_WORDS,
-                  hs + static_cast<size_t>(pd.out - lo) * VSG_STAT_WORDS, sizeof(int32_t) * VSG_STAT_WORDS);
-    }
-    if (want_cigar) {
-      int64_t total = 0;
-      for (int p = 0; p < np; p++) {
-        total = std::max<int64_t>(total, h_offs[p] + h_stats_all[static_cast<size_t>(ch.pairs[p].out) * VSG_STAT_WORDS + VSG_STAT_CIGARLEN] + 1);
-      }
-      dense.resize(static_cast<size_t>(total) + 1);
-      VSG_CUDA_OK(cudaMemcpyAsync(dense.data(), c->cigar_dense.p, static_cast<size_t>(total), cudaMemcpyDeviceToHost, c->stream));
-      VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
-      for (int p = 0; p < np; p++) {
-        (*cigars_out)[static_cast<size_t>(ch.pairs[p].out)] = std::string(dense.data() + h_offs[p]);
-      }
-    }
-  }
-  return VSG_OK;
-}
 
 }  // namespace
 
@@ -547,42 +405,79 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
   }
   if (npairs > (1LL << 30)) { Error::set("vsg_align_pairs: too many pairs in one call"); return VSG_EINVAL; }
   VSG_CUDA_OK(cudaSetDevice(c->device));
+  static const bool trace = std::getenv("VSG_TRACE") != nullptr;
+  auto const t_begin = std::chrono::steady_clock::now();
   bool const want_cigar = (cigar_buf != nullptr);
   if (want_cigar && cigar_off == nullptr) { Error::set("vsg_align_pairs: cigar_off required with cigar_buf"); return VSG_EINVAL; }
+  if (npairs == 0) { if (want_cigar) { cigar_off[0] = 0; } return VSG_OK; }
 
-  std::vector<int32_t> st(static_cast<size_t>(npairs) * VSG_STAT_WORDS, 0);
+  int rc;
+  // final home of the per-pair statistics: pinned, written by one D2H at the end (GPU pairs) and by
+  // the host directly (pairs resolved without DP)
+  if ((rc = c->h_stats.reserve(sizeof(int32_t) * VSG_STAT_WORDS * static_cast<size_t>(npairs))) != VSG_OK) { return rc; }
+  if ((rc = c->stats.reserve(sizeof(int32_t) * VSG_STAT_WORDS * static_cast<size_t>(npairs) + 64)) != VSG_OK) { return rc; }
+  int32_t * const hs = static_cast<int32_t *>(c->h_stats.p);
+  struct HostPair { int64_t slot; int32_t st[VSG_STAT_WORDS]; };
+  std::vector<HostPair> host_pairs;
   std::vector<std::string> cigars;
   if (want_cigar) { cigars.resize(static_cast<size_t>(npairs)); }
-  int rc;
-  if ((rc = c->stats.reserve(sizeof(int32_t) * VSG_STAT_WORDS * static_cast<size_t>(npairs) + 64)) != VSG_OK) { return rc; }
 
   ScoreParams const & sp = c->sp;
-  Chunk ch;
+  FastBound const fbound = fast_bound_of(sp);
+  std::vector<FastTask> all_fast;
+  std::vector<ExactTask> all_exact;
+  std::vector<PairDesc> all_pairs;  // CIGAR mode only
+  std::vector<ChunkPlan> plans;
+  ChunkBuilder cb;
+  all_fast.reserve(static_cast<size_t>(npairs) / 2 + 16);
   struct Cand { int64_t slot; uint32_t t; int32_t d; bool general; };
   std::vector<Cand> group_fast;
 
-  auto sentinel = [&](int64_t i) {
-    int32_t * s = &st[static_cast<size_t>(i) * VSG_STAT_WORDS];
-    std::memset(s, 0, sizeof(int32_t) * VSG_STAT_WORDS);
-    s[VSG_STAT_SCORE] = VSG_SCORE_SENTINEL;
+  auto host_pair = [&](int64_t slot) -> int32_t * {
+    host_pairs.emplace_back();
+    host_pairs.back().slot = slot;
+    std::memset(host_pairs.back().st, 0, sizeof(int32_t) * VSG_STAT_WORDS);
+    return host_pairs.back().st;
   };
 
-  auto flush_chunk = [&]() -> int {
-    if (ch.empty()) { return VSG_OK; }
-    int const r = run_chunk(c, queries, targets, ch, want_cigar, st.data(), want_cigar ? &cigars : nullptr);
-    ch.clear();
-    return r;
+  auto close_chunk = [&]() {
+    if (cb.empty()) { return; }
+    ChunkPlan pl;
+    for (int g = 0; g < 2; g++) {
+      for (int R = 1; R <= FAST_RMAX; R++) {
+        auto & v = cb.fast[g][R];
+        if (v.empty()) { continue; }
+        // longest first: the tail of the grid is made of the short ones
+        auto const longer = [](const FastTask & a, const FastTask & b) { return a.dmax > b.dmax; };
+        if (!std::is_sorted(v.begin(), v.end(), longer)) { std::sort(v.begin(), v.end(), longer); }
+        pl.runs.push_back(ClassRun{R, g != 0, all_fast.size(), static_cast<int>(v.size())});
+        all_fast.insert(all_fast.end(), v.begin(), v.end());
+        v.clear();
+      }
+    }
+    pl.exact_first = all_exact.size(); pl.exact_count = static_cast<int>(cb.exact.size());
+    all_exact.insert(all_exact.end(), cb.exact.begin(), cb.exact.end());
+    cb.exact.clear();
+    pl.pair_first = all_pairs.size() - static_cast<size_t>(cb.npairdesc); pl.pair_count = cb.npairdesc;
+    pl.dir_bytes = cb.dir_bytes; pl.bnd_elems = cb.bnd_elems; pl.he_elems = cb.he_elems; pl.cigar_bytes = cb.cigar_bytes;
+    pl.cells = cb.cells; pl.nfast = cb.nfast; pl.nexact = cb.nexact;
+    plans.push_back(std::move(pl));
+    cb.dir_bytes = cb.bnd_elems = cb.he_elems = cb.cigar_bytes = 0;
+    cb.cells = cb.nfast = cb.nexact = 0; cb.npairdesc = 0;
   };
 
   auto add_pairdesc = [&](uint32_t q, uint32_t t, int kind, int64_t slot, int R, int half, int dmax, uint64_t dir_off) {
+    if (!want_cigar) { return; }
     PairDesc pd{};
     pd.q = q; pd.t = t; pd.dir_off = dir_off; pd.kind = kind; pd.out = static_cast<int32_t>(slot);
     pd.R = R; pd.half = half; pd.dmax = dmax;
-    pd.cigar_off = ch.cigar_bytes;
-    ch.cigar_bytes += static_cast<uint64_t>(queries->h_len[q]) + static_cast<uint64_t>(targets->h_len[t]) + 2;
-    ch.pairs.push_back(pd);
+    pd.cigar_off = cb.cigar_bytes;
+    cb.cigar_bytes += static_cast<uint64_t>(queries->h_len[q]) + static_cast<uint64_t>(targets->h_len[t]) + 2;
+    all_pairs.push_back(pd);
+    cb.npairdesc++;
   };
 
+  // ---- plan: resolve trivial pairs on the host, group by query, pair targets two by two ----------
   int64_t i = 0;
   while (i < npairs) {
     uint32_t const q = qidx[i];
@@ -596,10 +491,9 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
       uint32_t const t = tidx[k];
       if (t >= static_cast<uint64_t>(targets->d.n)) { Error::set("vsg_align_pairs: target index out of range"); return VSG_EINVAL; }
       int const D = targets->h_len[t];
-      if (sp.fallback) { sentinel(k); continue; }  // align_simd.cpp:1463-1479
-      if (Q == 0) {                                // align_simd.cpp:1481-1539
-        int32_t * s = &st[static_cast<size_t>(k) * VSG_STAT_WORDS];
-        std::memset(s, 0, sizeof(int32_t) * VSG_STAT_WORDS);
+      if (sp.fallback) { host_pair(k)[VSG_STAT_SCORE] = VSG_SCORE_SENTINEL; continue; }  // align_simd.cpp:1463-1479
+      if (Q == 0) {                                                                      // align_simd.cpp:1481-1539
+        int32_t * s = host_pair(k);
         if (!fits16(0, D)) { s[VSG_STAT_SCORE] = VSG_SCORE_SENTINEL; continue; }
         s[VSG_STAT_ALIGNED] = D; s[VSG_STAT_GAPS] = D;
         if (D > 0) {
@@ -612,32 +506,33 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
         }
         continue;
       }
-      if (D == 0 || !fits16(Q, D)) { sentinel(k); continue; }  // align_simd.cpp:1867-1882
+      if (D == 0 || !fits16(Q, D)) { host_pair(k)[VSG_STAT_SCORE] = VSG_SCORE_SENTINEL; continue; }  // :1867-1882
       bool const general = q_general || targets->h_nonacgt[t] != 0;
       int R, ns;
       fast_shape(Q, general, R, ns);
-      if (!c->fast_disabled && fast_path_ok(sp, ns * 32 * R, D)) {
+      if (!c->fast_disabled && fast_path_ok(fbound, ns * 32 * R, D)) {
         group_fast.push_back(Cand{k, t, D, general});
       } else {
         uint64_t const dirb = align_up(static_cast<uint64_t>(Q) * D, 16);
-        if (!ch.empty() && ch.dir_bytes + dirb > c->dir_budget) { if ((rc = flush_chunk()) != VSG_OK) { return rc; } }
+        if (!cb.empty() && cb.dir_bytes + dirb > c->dir_budget) { close_chunk(); }
         ExactTask et{};
         et.q = q; et.t = t; et.out = static_cast<int32_t>(k);
-        et.dir_off = ch.dir_bytes; et.he_off = ch.he_elems;
-        add_pairdesc(q, t, 1, k, 0, 0, 0, ch.dir_bytes);
-        ch.dir_bytes += dirb;
-        ch.he_elems += 2ULL * Q;
-        ch.exact.push_back(et);
-        ch.cells += static_cast<int64_t>(Q) * D; ch.nexact++;
+        et.dir_off = cb.dir_bytes; et.he_off = cb.he_elems;
+        add_pairdesc(q, t, 1, k, 0, 0, 0, cb.dir_bytes);
+        cb.dir_bytes += dirb;
+        cb.he_elems += 2ULL * Q;
+        cb.exact.push_back(et);
+        cb.cells += static_cast<int64_t>(Q) * D; cb.nexact++;
       }
     }
-    // pair the fast candidates two by two, similar lengths together
     if (!group_fast.empty()) {
-      std::sort(group_fast.begin(), group_fast.end(), [](const Cand & a, const Cand & b) {
+      // similar lengths together (a warp runs for the longer of its two targets)
+      auto const by_len = [](const Cand & a, const Cand & b) {
         if (a.general != b.general) { return a.general < b.general; }
         if (a.d != b.d) { return a.d > b.d; }
         return a.slot < b.slot;
-      });
+      };
+      if (!std::is_sorted(group_fast.begin(), group_fast.end(), by_len)) { std::sort(group_fast.begin(), group_fast.end(), by_len); }
       size_t k = 0;
       while (k < group_fast.size()) {
         Cand const & a = group_fast[k];
@@ -647,31 +542,146 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
         fast_shape(Q, a.general, R, ns);
         int const dmax = std::max(a.d, b.d);
         uint64_t const dirb = static_cast<uint64_t>(ns) * (dmax + 31) * 32 * fast_rw(R) * 4;
-        if (!ch.empty() && ch.dir_bytes + dirb > c->dir_budget) { if ((rc = flush_chunk()) != VSG_OK) { return rc; } }
+        if (!cb.empty() && cb.dir_bytes + dirb > c->dir_budget) { close_chunk(); }
         FastTask ft{};
         ft.q = q; ft.tlo = a.t; ft.thi = b.t;
         ft.out_lo = static_cast<int32_t>(a.slot);
         ft.out_hi = pair2 ? static_cast<int32_t>(b.slot) : -1;
         ft.dmax = dmax;
-        ft.dir_off = ch.dir_bytes;
-        ft.bnd_off = ch.bnd_elems;
-        add_pairdesc(q, a.t, 0, a.slot, R, 0, dmax, ch.dir_bytes);
-        if (pair2) { add_pairdesc(q, b.t, 0, b.slot, R, 1, dmax, ch.dir_bytes); }
-        ch.dir_bytes += dirb;
-        if (ns > 1) { ch.bnd_elems += static_cast<uint64_t>(dmax); }
-        ch.fast[a.general ? 1 : 0][R].push_back(ft);
-        ch.cells += static_cast<int64_t>(Q) * a.d + (pair2 ? static_cast<int64_t>(Q) * b.d : 0);
-        ch.nfast += pair2 ? 2 : 1;
+        ft.dir_off = cb.dir_bytes;
+        ft.bnd_off = cb.bnd_elems;
+        add_pairdesc(q, a.t, 0, a.slot, R, 0, dmax, cb.dir_bytes);
+        if (pair2) { add_pairdesc(q, b.t, 0, b.slot, R, 1, dmax, cb.dir_bytes); }
+        cb.dir_bytes += dirb;
+        if (ns > 1) { cb.bnd_elems += static_cast<uint64_t>(dmax); }
+        cb.fast[a.general ? 1 : 0][R].push_back(ft);
+        cb.cells += static_cast<int64_t>(Q) * a.d + (pair2 ? static_cast<int64_t>(Q) * b.d : 0);
+        cb.nfast += pair2 ? 2 : 1;
         k += pair2 ? 2 : 1;
       }
     }
     i = j;
   }
-  if ((rc = flush_chunk()) != VSG_OK) { return rc; }
+  close_chunk();
+  auto const t_planned = std::chrono::steady_clock::now();
+
+  // ---- upload every task of the call once; size the scratch for the largest chunk ----------------
+  uint64_t max_dir = 0, max_bnd = 0, max_he = 0, max_cig = 0;
+  for (auto const & pl : plans) {
+    max_dir = std::max(max_dir, pl.dir_bytes); max_bnd = std::max(max_bnd, pl.bnd_elems);
+    max_he = std::max(max_he, pl.he_elems); max_cig = std::max(max_cig, pl.cigar_bytes);
+  }
+  if (!plans.empty()) {
+    if ((rc = c->dir.reserve(max_dir + 256)) != VSG_OK) { return rc; }
+    if ((rc = c->bnd.reserve(sizeof(uint2) * (max_bnd + 1))) != VSG_OK) { return rc; }
+    if ((rc = c->he.reserve(sizeof(int16_t) * (max_he + 1))) != VSG_OK) { return rc; }
+    if ((rc = c->tasks_fast.reserve(sizeof(FastTask) * (all_fast.size() + 1))) != VSG_OK) { return rc; }
+    if ((rc = c->tasks_exact.reserve(sizeof(ExactTask) * (all_exact.size() + 1))) != VSG_OK) { return rc; }
+    size_t const fb = sizeof(FastTask) * all_fast.size(), eb = sizeof(ExactTask) * all_exact.size();
+    if ((rc = c->h_tasks.reserve(fb + eb + 64)) != VSG_OK) { return rc; }
+    char * hp = static_cast<char *>(c->h_tasks.p);
+    if (fb > 0) {
+      std::memcpy(hp, all_fast.data(), fb);
+      VSG_CUDA_OK(cudaMemcpyAsync(c->tasks_fast.p, hp, fb, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (eb > 0) {
+      std::memcpy(hp + fb, all_exact.data(), eb);
+      VSG_CUDA_OK(cudaMemcpyAsync(c->tasks_exact.p, hp + fb, eb, cudaMemcpyHostToDevice, c->stream));
+    }
+  }
+  // events: 3 per chunk
+  while (c->ev_pool.size() < 3 * plans.size()) {
+    cudaEvent_t e;
+    VSG_CUDA_OK(cudaEventCreate(&e));
+    c->ev_pool.push_back(e);
+  }
+
+  FastTask * const d_fast = static_cast<FastTask *>(c->tasks_fast.p);
+  ExactTask * const d_exact = static_cast<ExactTask *>(c->tasks_exact.p);
+  int32_t * const d_stats = static_cast<int32_t *>(c->stats.p);
+  uint8_t * const d_dir = static_cast<uint8_t *>(c->dir.p);
+
+  for (size_t ci = 0; ci < plans.size(); ci++) {
+    ChunkPlan const & pl = plans[ci];
+    VSG_CUDA_OK(cudaEventRecord(c->ev_pool[3 * ci], c->stream));
+    for (auto const & run : pl.runs) { launch_fast(c, run.R, run.general, queries->d, targets->d, d_fast + run.first, run.count); }
+    if (pl.exact_count > 0) {
+      nw_exact_kernel<<<(pl.exact_count + 63) / 64, 64, 0, c->stream>>>(sp, queries->d, targets->d, d_exact + pl.exact_first,
+                                                                        pl.exact_count, d_dir, static_cast<int16_t *>(c->he.p), d_stats);
+      count_launch();
+    }
+    VSG_CUDA_OK(cudaEventRecord(c->ev_pool[3 * ci + 1], c->stream));
+    if (!want_cigar) {
+      for (auto const & run : pl.runs) {
+        int const nthr = 2 * run.count;
+        traceback_fast_tasks_kernel<<<(nthr + 127) / 128, 128, 0, c->stream>>>(sp, queries->d, targets->d, d_fast + run.first,
+                                                                               run.count, run.R, d_dir, d_stats);
+        count_launch();
+      }
+      if (pl.exact_count > 0) {
+        traceback_exact_tasks_kernel<<<(pl.exact_count + 127) / 128, 128, 0, c->stream>>>(sp, queries->d, targets->d,
+                                                                                         d_exact + pl.exact_first, pl.exact_count, d_dir, d_stats);
+        count_launch();
+      }
+      VSG_CUDA_OK(cudaEventRecord(c->ev_pool[3 * ci + 2], c->stream));
+    } else {
+      // CIGAR texts: descriptors up, traceback with text, dense packing, texts home — per chunk
+      int const np = pl.pair_count;
+      if ((rc = c->pairs.reserve(sizeof(PairDesc) * (static_cast<size_t>(np) + 1))) != VSG_OK) { return rc; }
+      if ((rc = c->cigar_scratch.reserve(pl.cigar_bytes + 64)) != VSG_OK) { return rc; }
+      if ((rc = c->cigar_dense.reserve(pl.cigar_bytes + 64)) != VSG_OK) { return rc; }
+      if ((rc = c->cigar_len.reserve(sizeof(int64_t) * (static_cast<size_t>(np) + 1))) != VSG_OK) { return rc; }
+      if ((rc = c->cigar_offs.reserve(sizeof(int64_t) * (static_cast<size_t>(np) + 1))) != VSG_OK) { return rc; }
+      PairDesc const * hpairs = all_pairs.data() + pl.pair_first;
+      PairDesc * d_pairs = static_cast<PairDesc *>(c->pairs.p);
+      VSG_CUDA_OK(cudaMemcpyAsync(d_pairs, hpairs, sizeof(PairDesc) * np, cudaMemcpyHostToDevice, c->stream));
+      traceback_kernel<true><<<(np + 127) / 128, 128, 0, c->stream>>>(sp, queries->d, targets->d, d_pairs, np, d_dir,
+                                                                      static_cast<char *>(c->cigar_scratch.p), d_stats);
+      count_launch();
+      VSG_CUDA_OK(cudaEventRecord(c->ev_pool[3 * ci + 2], c->stream));
+      cigar_len_kernel<<<(np + 255) / 256, 256, 0, c->stream>>>(d_pairs, d_stats, np, static_cast<int64_t *>(c->cigar_len.p));
+      count_launch();
+      size_t tmp_bytes = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, static_cast<int64_t *>(c->cigar_len.p),
+                                    static_cast<int64_t *>(c->cigar_offs.p), np, c->stream);
+      if ((rc = c->cub_tmp.reserve(tmp_bytes + 16)) != VSG_OK) { return rc; }
+      cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, static_cast<int64_t *>(c->cigar_len.p),
+                                    static_cast<int64_t *>(c->cigar_offs.p), np, c->stream);
+      count_launch();
+      cigar_gather_kernel<<<np, 64, 0, c->stream>>>(d_pairs, np, queries->d, targets->d, d_stats,
+                                                    static_cast<int64_t *>(c->cigar_offs.p),
+                                                    static_cast<char *>(c->cigar_scratch.p), static_cast<char *>(c->cigar_dense.p));
+      count_launch();
+      std::vector<int64_t> h_offs(static_cast<size_t>(np)), h_lens(static_cast<size_t>(np));
+      VSG_CUDA_OK(cudaMemcpyAsync(h_offs.data(), c->cigar_offs.p, sizeof(int64_t) * np, cudaMemcpyDeviceToHost, c->stream));
+      VSG_CUDA_OK(cudaMemcpyAsync(h_lens.data(), c->cigar_len.p, sizeof(int64_t) * np, cudaMemcpyDeviceToHost, c->stream));
+      VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+      int64_t const total = np > 0 ? h_offs[static_cast<size_t>(np) - 1] + h_lens[static_cast<size_t>(np) - 1] : 0;
+      std::vector<char> dense(static_cast<size_t>(total) + 1);
+      if (total > 0) {
+        VSG_CUDA_OK(cudaMemcpyAsync(dense.data(), c->cigar_dense.p, static_cast<size_t>(total), cudaMemcpyDeviceToHost, c->stream));
+        VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+      }
+      for (int p = 0; p < np; p++) { cigars[static_cast<size_t>(hpairs[p].out)] = std::string(dense.data() + h_offs[static_cast<size_t>(p)]); }
+    }
+  }
+  if (!plans.empty()) {
+    VSG_CUDA_OK(cudaMemcpyAsync(hs, d_stats, sizeof(int32_t) * VSG_STAT_WORDS * static_cast<size_t>(npairs), cudaMemcpyDeviceToHost, c->stream));
+  }
+  VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+  VSG_CUDA_OK(cudaGetLastError());
+  for (size_t ci = 0; ci < plans.size(); ci++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev_pool[3 * ci], c->ev_pool[3 * ci + 1]) == cudaSuccess) { c->prof_fwd_ms += ms; }
+    if (cudaEventElapsedTime(&ms, c->ev_pool[3 * ci + 1], c->ev_pool[3 * ci + 2]) == cudaSuccess) { c->prof_tb_ms += ms; }
+    c->prof_cells += plans[ci].cells; c->prof_fast += plans[ci].nfast; c->prof_exact += plans[ci].nexact;
+    c->prof_fwd_launches += static_cast<int64_t>(plans[ci].runs.size()) + (plans[ci].exact_count > 0 ? 1 : 0);
+  }
+  for (auto const & hp : host_pairs) { std::memcpy(hs + static_cast<size_t>(hp.slot) * VSG_STAT_WORDS, hp.st, sizeof(int32_t) * VSG_STAT_WORDS); }
 
   int64_t cpos = 0;
   for (int64_t k = 0; k < npairs; k++) {
-    int32_t const * s = &st[static_cast<size_t>(k) * VSG_STAT_WORDS];
+    int32_t const * s = hs + static_cast<size_t>(k) * VSG_STAT_WORDS;
     score[k] = static_cast<int16_t>(s[VSG_STAT_SCORE]);
     if (aligned != nullptr) { aligned[k] = static_cast<uint16_t>(s[VSG_STAT_ALIGNED]); }
     if (matches != nullptr) { matches[k] = static_cast<uint16_t>(s[VSG_STAT_MATCHES]); }
@@ -693,6 +703,13 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
     }
   }
   if (want_cigar) { cigar_off[npairs] = cpos; }
+  if (trace) {
+    auto const t_end = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[vsg trace] align_pairs %lld pairs, %zu chunk(s): plan %.1f ms, total %.1f ms\n",
+                 static_cast<long long>(npairs), plans.size(),
+                 std::chrono::duration<double, std::milli>(t_planned - t_begin).count(),
+                 std::chrono::duration<double, std::milli>(t_end - t_begin).count());
+  }
   return VSG_OK;
 }
 

@@ -124,5 +124,6 @@ struct vsg_ctx {
   int64_t prof_cells = 0, prof_fast = 0, prof_exact = 0, prof_fwd_launches = 0;
   float prof_fwd_ms = 0.f, prof_tb_ms = 0.f, prof_rank_ms = 0.f;
   bool rank_pending = false;
+  std::vector<cudaEvent_t> ev_pool;  // 3 per chunk of an align call
   std::vector<vsg_ctx *> children;  // per-host-thread contexts of vsg_search_batch
 };
