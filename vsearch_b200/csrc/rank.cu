@@ -162,6 +162,7 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
   uint32_t * const lbeg = kmers + KMER_CAP;                                       // KMER_CAP
   uint32_t * const llen = lbeg + KMER_CAP;                                        // KMER_CAP
   __shared__ int s_ncand, s_nk;
+  __shared__ int s_wsum[RANK_THREADS / 32];
 
   int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NWARPS = RANK_THREADS / 32;
@@ -219,15 +220,18 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
       //    before it touches a counter: six independent HBM requests per lane hide the latency that a
       //    one-list-at-a-time loop exposes once per list (the typical list is ~70 vectors long).
       //    Padding entries land in the dummy word counters[SHARD/2].
-      for (int i = warp; i < np2; i += 2 * NWARPS) {
-        int const i2 = i + NWARPS;
-        uint32_t const na = llen[i] >> 3;
-        uint32_t const nb = (i2 < np2) ? (llen[i2] >> 3) : 0u;
-        const uint4 * __restrict__ pa = reinterpret_cast<const uint4 *>(S.post + lbeg[i]);
-        const uint4 * __restrict__ pb = reinterpret_cast<const uint4 *>(S.post + (i2 < np2 ? lbeg[i2] : 0u));
-        uint32_t const nmax = na > nb ? na : nb;
-        for (uint32_t base = 0; base < nmax; base += 96) {
-          uint4 x[6];
+      {
+        auto pair_len = [&](int li) -> uint32_t {
+          uint32_t const na = llen[li] >> 3;
+          uint32_t const nb = (li + NWARPS < np2) ? (llen[li + NWARPS] >> 3) : 0u;
+          return na > nb ? na : nb;
+        };
+        auto load_set = [&](int li, uint32_t base, uint4 (&x)[6]) {
+          int const l2 = li + NWARPS;
+          uint32_t const na = llen[li] >> 3;
+          uint32_t const nb = (l2 < np2) ? (llen[l2] >> 3) : 0u;
+          const uint4 * __restrict__ pa = reinterpret_cast<const uint4 *>(S.post + lbeg[li]);
+          const uint4 * __restrict__ pb = reinterpret_cast<const uint4 *>(S.post + (l2 < np2 ? lbeg[l2] : 0u));
 #pragma unroll
           for (int u = 0; u < 3; u++) {
             uint32_t const e = base + lane + 32u * u;
@@ -236,10 +240,25 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
             if (e < na) { x[u] = __ldg(pa + e); }
             if (e < nb) { x[3 + u] = __ldg(pb + e); }
           }
+        };
+        // software pipeline: the loads of the next (list pair, offset) are in flight while the
+        // counters of the current one are updated
+        int li = warp;
+        uint32_t base = 0;
+        bool have = li < np2;
+        uint4 cur[6];
+        if (have) { load_set(li, base, cur); }
+        while (have) {
+          int nli = li;
+          uint32_t nbase = base + 96;
+          if (nbase >= pair_len(li)) { nli = li + 2 * NWARPS; nbase = 0; }
+          bool const nhave = nli < np2;
+          uint4 nxt[6];
+          if (nhave) { load_set(nli, nbase, nxt); }
 #pragma unroll
           for (int u = 0; u < 6; u++) {
-            uint32_t const w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
-            if (w[0] == 0x80008000u && w[3] == 0x80008000u) { continue; }  // nothing loaded (lists are short)
+            uint32_t const w[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
+            if (w[0] == 0x80008000u) { continue; }  // padding only (real entries come first)
 #pragma unroll
             for (int k = 0; k < 4; k++) {
               uint32_t const a = w[k] & 0xffffu, b = w[k] >> 16;
@@ -247,11 +266,52 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
               atomicAdd(&counters[b >> 1], (b & 1) ? 0x10000u : 1u);
             }
           }
+#pragma unroll
+          for (int u = 0; u < 6; u++) { cur[u] = nxt[u]; }
+          li = nli; base = nbase; have = nhave;
         }
       }
       __syncthreads();
-      // 4. threshold scan in segments; sort-and-cut the candidate list when it could overflow
+      // 4. threshold scan.  Common case: count the survivors, one block-wide prefix sum, write them
+      //    straight to their slots (no barrier per segment).  Only if they would not fit does the
+      //    segmented sort-and-cut path below run.
       int const nwords = (S.nt + 1) >> 1;
+      {
+        int mycount = 0;
+        for (int wi = threadIdx.x; wi < nwords; wi += blockDim.x) {
+          uint32_t const w = counters[wi];
+          mycount += ((w & 0xffffu) >= minmatches && 2 * wi < S.nt) + ((w >> 16) >= minmatches && 2 * wi + 1 < S.nt);
+        }
+        int incl = mycount;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int const o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) { incl += o; } }
+        if (lane == 31) { s_wsum[warp] = incl; }
+        __syncthreads();
+        int wbase = 0, total = 0;
+        for (int w2 = 0; w2 < NWARPS; w2++) { int const v = s_wsum[w2]; if (w2 < warp) { wbase += v; } total += v; }
+        int const level = s_ncand;
+        __syncthreads();
+        if (level + total <= CAND_CAP) {
+          int pos = level + wbase + incl - mycount;
+          for (int wi = threadIdx.x; wi < nwords; wi += blockDim.x) {
+            uint32_t const w = counters[wi];
+            uint32_t const c0 = w & 0xffffu, c1 = w >> 16;
+            int const lt0 = 2 * wi, lt1 = 2 * wi + 1;
+            if (c0 >= minmatches && lt0 < S.nt) {
+              int const t = S.t0 + lt0;
+              cand[pos++] = make_key(c0, static_cast<uint32_t>(db.len[t]), static_cast<uint32_t>(t));
+            }
+            if (c1 >= minmatches && lt1 < S.nt) {
+              int const t = S.t0 + lt1;
+              cand[pos++] = make_key(c1, static_cast<uint32_t>(db.len[t]), static_cast<uint32_t>(t));
+            }
+          }
+          if (threadIdx.x == 0) { s_ncand = level + total; }
+          __syncthreads();
+          continue;  // next shard
+        }
+      }
+      // 4b. segmented scan with sort-and-cut when the candidate list could overflow
       for (int seg = 0; seg < nwords; seg += SCAN_SEG_WORDS) {
         // every thread must take the same decision: read the fill level, then fence the read off
         // from the appends of threads that are already past this point
