@@ -1,0 +1,14 @@
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from vsearch_b200 import lib as vlib, synth
+NQ = 65536
+dbm = synth.config2_db(100_000, 1500, 2024)
+ctx = vlib.Context(0)
+db = ctx.seqset(synth.SeqSet.from_matrix(dbm)); ix = ctx.index(db, 8, 0)
+qs_h, _ = synth.config2_query_batch(dbm, NQ, batch=1); qs = ctx.seqset(qs_h)
+opts = vlib.default_search_opts(); opts.id = 0.9
+best = 1e9
+for rep in range(5):
+    t0 = time.time(); r, c, w = ctx.search(ix, db, qs, 0, NQ, opts, 1); best = min(best, time.time() - t0)
+print(f"{1e3*best:.1f} ms  {w[1]/best/1e9:.0f} GCUPS  {NQ/best/1e3:.0f} kq/s")

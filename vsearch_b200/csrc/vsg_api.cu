@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <map>
+#include <mutex>
 #include <chrono>
 
 namespace vsg {
@@ -21,12 +23,47 @@ void Error::set(const std::string & m) { g_last_error = m; }
 static std::atomic<int64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Device buffers come from a small per-device cache of freed blocks: query batches, reverse
+// complements and scratch come and go every call, and cudaMalloc/cudaFree are expensive —
+// dramatically so once NCCL has enabled peer access between the GPUs of a box.
+namespace {
+struct PoolKey { int device; size_t cls; bool operator<(const PoolKey & o) const { return device != o.device ? device < o.device : cls < o.cls; } };
+std::mutex g_pool_mutex;
+std::multimap<PoolKey, void *> g_pool;
+size_t size_class(size_t bytes)
+{
+  size_t const GB = static_cast<size_t>(1) << 30;
+  if (bytes > GB) { return (bytes + GB - 1) / GB * GB; }
+  size_t c = 1 << 16;
+  while (c < bytes) { c <<= 1; }
+  return c;
+}
+}  // namespace
+
 int DevBuf::reserve(size_t bytes)
 {
   if (bytes <= cap) { return VSG_OK; }
-  if (p != nullptr) { cudaFree(p); p = nullptr; cap = 0; }
-  size_t const want = bytes + bytes / 8 + 256;
-  cudaError_t const e = cudaMalloc(&p, want);
+  release();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t const want = size_class(bytes + 256);
+  {
+    std::lock_guard<std::mutex> const lock(g_pool_mutex);
+    auto it = g_pool.find(PoolKey{dev, want});
+    if (it != g_pool.end()) { p = it->second; cap = want; g_pool.erase(it); return VSG_OK; }
+  }
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    // give the cache back to the driver and retry once
+    cudaGetLastError();
+    {
+      std::lock_guard<std::mutex> const lock(g_pool_mutex);
+      for (auto it = g_pool.begin(); it != g_pool.end();) {
+        if (it->first.device == dev) { cudaFree(it->second); it = g_pool.erase(it); } else { ++it; }
+      }
+    }
+    e = cudaMalloc(&p, want);
+  }
   if (e != cudaSuccess) {
     p = nullptr;
     Error::set(std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
@@ -35,7 +72,15 @@ int DevBuf::reserve(size_t bytes)
   cap = want;
   return VSG_OK;
 }
-void DevBuf::release() { if (p != nullptr) { cudaFree(p); p = nullptr; cap = 0; } }
+void DevBuf::release()
+{
+  if (p == nullptr) { return; }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> const lock(g_pool_mutex);
+  g_pool.emplace(PoolKey{dev, cap}, p);
+  p = nullptr; cap = 0;
+}
 
 int PinBuf::reserve(size_t bytes)
 {
@@ -167,6 +212,12 @@ extern "C" int vsg_ctx_create(int device, const vsg_scoring * scoring, vsg_ctx *
   const char * db = std::getenv("VSG_DIR_BUDGET_MB");
   if (db != nullptr && std::atoll(db) > 0) { c->dir_budget = static_cast<size_t>(std::atoll(db)) << 20; }
   VSG_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    VSG_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    VSG_CUDA_OK(cudaStreamCreateWithPriority(&c->stream_hi, cudaStreamNonBlocking, hi));
+    VSG_CUDA_OK(cudaEventCreateWithFlags(&c->ev_hi, cudaEventDisableTiming));
+  }
   for (auto & ev : c->ev) { VSG_CUDA_OK(cudaEventCreate(&ev)); }
   // the fast kernel leans on VIMNMX.S16x2 predicate semantics: check them on this device once
   int * d_bad = nullptr;
@@ -199,6 +250,8 @@ extern "C" void vsg_ctx_destroy(vsg_ctx * c)
   for (PinBuf * b : {&c->h_tasks, &c->h_stats, &c->h_pairs, &c->h_misc}) { b->release(); }
   for (auto & ev : c->ev) { if (ev != nullptr) { cudaEventDestroy(ev); } }
   for (auto & ev : c->ev_pool) { cudaEventDestroy(ev); }
+  if (c->stream_hi != nullptr) { cudaStreamDestroy(c->stream_hi); }
+  if (c->ev_hi != nullptr) { cudaEventDestroy(c->ev_hi); }
   if (c->stream != nullptr) { cudaStreamDestroy(c->stream); }
   delete c;
 }

@@ -111,6 +111,8 @@ struct vsg_seqset {
 struct vsg_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_hi = nullptr;  // high priority: ranker kernels interleave with forward-DP grids
+  cudaEvent_t ev_hi = nullptr;
   vsg_scoring scoring{};
   vsg::ScoreParams sp{};
   bool fast_disabled = false;  // VSG_DISABLE_FAST=1 (tests force the exact kernel)
