@@ -283,6 +283,14 @@ def main():
     int_peak_gcups = 2.0 * peak_ops / 15.0 / 1e9   # 2 cells per packed op, 15 ops per cell (align_simd.cpp:765-780)
     dir_bytes_per_cell = 0.5 * (DB_LEN + 31) / DB_LEN * 256 / 250   # 4 bits/cell + wavefront and row padding
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:   # dram bytes of one launch from the committed ncu --set full capture, scaled to this launch's cells
+        tj = json.load(open(os.path.join(ROOT, "profiles", "nw_fast_r01_traffic.json")))
+        per_cell = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["cells_per_launch"]
+        traffic = {"bytes_per_launch": per_cell * res_r.cells / max(1, prof_r.fwd_launches), "bytes_per_cell": per_cell,
+                   "source": "profiles/nw_fast_r01.ncu-rep"}
+    except Exception:
+        pass
     roofline = {"bound": "int_alu", "kernel": "nw_fast_kernel<8,false>",
                 "achieved": fwd_gcups, "peak": int_peak_gcups, "unit": "GCUPS", "frac": fwd_gcups / int_peak_gcups,
                 "peak_source": "vsg_measure_int_peak (VIMNMX.S16x2+VIADD.16x2 lane-ops/s, measured live, burst) x2 cells /15 ops",
@@ -293,7 +301,7 @@ def main():
                         "frac": fwd_gcups * dir_bytes_per_cell / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
                         "algorithmic_bytes_per_cell": dir_bytes_per_cell},
-                "traffic": None,
+                "traffic": traffic,
                 "alone_ms": {"forward": res_r.fwd_ms, "traceback": res_r.tb_ms, "rank": rank_ms_alone,
                              "queries": nq_r, "pairs": int(qi.shape[0])},
                 "in_step_kernel_ms_overlapping_streams": {"forward": prof.fwd_ms, "traceback": prof.traceback_ms,
