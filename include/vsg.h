@@ -175,6 +175,29 @@ int vsg_search_batch(vsg_ctx * ctx, const vsg_index * ix, const vsg_seqset * db,
                      const vsg_search_opts * opts, vsg_search_result * results, int max_results,
                      int32_t * counts, int64_t * work);
 
+/* ---- all-against-all: replaces the per-query body of allpairs_thread_run
+ *      (commands/allpairs_global.cpp:340-549) for query rows [row0, row0+nrows) of `set`: every
+ *      target j > i is aligned (no k-mer filter, default pre-alignment filters), a pair is kept iff
+ *      search_acceptable_aligned accepts it (id >= opts->id under opts->iddef), kept pairs of a
+ *      query are ordered by (id desc, target asc) as allpairs_hit_compare does, queries ascending.
+ *      hits: caller-allocated, `cap` records; *nhits receives the number produced (VSG_ECAP if it
+ *      exceeds cap).  Rows are independent, so N GPUs take disjoint row ranges.
+ *      work (optional, 2 x int64): pairs and DP cells aligned. ---- */
+typedef struct vsg_pair_hit {
+  int32_t query;
+  int32_t target;
+  int32_t matches;
+  int32_t mismatches;
+  int32_t gaps;
+  int32_t alignment_length;
+  int32_t nwscore;
+  int32_t internal_alignment_length;
+  double id;
+} vsg_pair_hit;
+int vsg_allpairs(vsg_ctx * ctx, const vsg_seqset * set, int64_t row0, int64_t nrows,
+                 const vsg_search_opts * opts, vsg_pair_hit * hits, int64_t cap, int64_t * nhits,
+                 int64_t * work);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,3 +74,31 @@ def test_usearch_global_and_cluster_fast(tmp_path):
         run(binary, ["--cluster_fast", cf, "--id", "0.97", "--uc", uc], 2)
         ucs[name] = sorted_lines(uc)
     assert len(ucs["cpu"]) > 3000 and ucs["cpu"] == ucs["gpu"]
+
+
+@pytest.mark.skipif(not os.path.exists(STOCK), reason="oracle/_ref/vsearch not built")
+def test_allpairs_api_vs_reference_cli(tmp_path):
+    """vsg_allpairs (rows sharded in two halves, as two GPUs would) against the stock CLI on configs[0]"""
+    from vsearch_b200 import lib as vlib
+    reads = synth.config1_allpairs()
+    fa = str(tmp_path / "c1.fasta")
+    synth.write_fasta(fa, reads, "r")
+    uo = str(tmp_path / "cpu.userout")
+    run(STOCK, ["--allpairs_global", fa, "--id", "0.8", "--qmask", "none", "--userout", uo,
+                "--userfields", "query+target+id+alnlen+mism+raw+ids"], os.cpu_count())
+    want = sorted_lines(uo)
+    ctx = vlib.Context(0)
+    ss = ctx.seqset(reads)
+    o = vlib.default_search_opts(); o.id = 0.8
+    n = len(reads)
+    h1, w1 = vlib.allpairs(ctx, ss, 0, 300, o, 200000)
+    h2, w2 = vlib.allpairs(ctx, ss, 300, n - 300, o, 200000)
+    # userout's alnlen is the alignment length without terminal gaps (results.cpp / userfields)
+    got = sorted(f"r{h['query']}\tr{h['target']}\t{h['id']:.1f}\t{h['internal_alignment_length']}\t{h['mismatches']}\t"
+                 f"{h['nwscore']}\t{h['matches']}\n" for h in list(h1) + list(h2))
+    assert len(want) > 10000 and got == want
+    assert int(w1[0] + w2[0]) == n * (n - 1) // 2
+    # per query: id descending, then target ascending (allpairs_hit_compare)
+    q = h1["query"]; same = q[1:] == q[:-1]
+    assert np.all((h1["id"][1:] <= h1["id"][:-1]) | ~same)
+    ss.close(); ctx.close()

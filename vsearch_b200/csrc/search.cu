@@ -408,3 +408,148 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   if (work != nullptr) { work[0] = total_pairs; work[1] = total_cells; }
   return VSG_OK;
 }
+
+
+// ---- all-against-all -----------------------------------------------------------------------------
+extern "C" int vsg_allpairs(vsg_ctx * c, const vsg_seqset * set, int64_t row0, int64_t nrows,
+                            const vsg_search_opts * opts, vsg_pair_hit * hits, int64_t cap, int64_t * nhits,
+                            int64_t * work)
+{
+  if (c == nullptr || set == nullptr || opts == nullptr || nhits == nullptr || (cap > 0 && hits == nullptr)) {
+    Error::set("vsg_allpairs: bad argument");
+    return VSG_EINVAL;
+  }
+  int64_t const n = set->d.n;
+  if (row0 < 0 || nrows < 0 || row0 + nrows > n) { Error::set("vsg_allpairs: row range out of bounds"); return VSG_EINVAL; }
+  if (opts->iddef < 0 || opts->iddef > 4) { Error::set("vsg_allpairs: iddef must be 0..4"); return VSG_EINVAL; }
+  double const opt_id = opts->id;
+  double const opt_weak_id = (opts->id >= 0.0 && opts->weak_id > opts->id) ? opts->id : opts->weak_id;
+  *nhits = 0;
+
+  // blocks of consecutive rows with about PAIRS_PER_BLOCK pairs each, handed to host threads that own
+  // a child context each; every block writes its hits to a private vector, concatenated in row order
+  int64_t const PAIRS_PER_BLOCK = 1 << 20;
+  std::vector<int64_t> block_first;
+  {
+    int64_t acc = 0;
+    block_first.push_back(row0);
+    for (int64_t i = row0; i < row0 + nrows; i++) {
+      acc += n - i - 1;
+      if (acc >= PAIRS_PER_BLOCK && i + 1 < row0 + nrows) { block_first.push_back(i + 1); acc = 0; }
+    }
+    block_first.push_back(row0 + nrows);
+  }
+  int64_t const nblocks = static_cast<int64_t>(block_first.size()) - 1;
+  int nthreads = 4;
+  if (const char * e = std::getenv("VSG_HOST_THREADS")) { nthreads = std::max(1, std::atoi(e)); }
+  nthreads = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nthreads, nblocks)));
+  while (static_cast<int>(c->children.size()) < nthreads) {
+    vsg_ctx * ch = nullptr;
+    int const r = vsg_ctx_create(c->device, &c->scoring, &ch);
+    if (r != VSG_OK) { return r; }
+    c->children.push_back(ch);
+  }
+  for (int t = 0; t < nthreads; t++) {
+    c->children[static_cast<size_t>(t)]->dir_budget = std::max<size_t>(c->dir_budget / static_cast<size_t>(nthreads), static_cast<size_t>(1) << 30);
+    c->children[static_cast<size_t>(t)]->fast_disabled = c->fast_disabled;
+  }
+  std::vector<std::vector<vsg_pair_hit>> out(static_cast<size_t>(nblocks));
+  std::vector<int64_t> bpairs(static_cast<size_t>(nblocks), 0), bcells(static_cast<size_t>(nblocks), 0);
+
+  auto run_block = [&](vsg_ctx * wc, int64_t bi) -> int {
+    int64_t const r0 = block_first[static_cast<size_t>(bi)], r1 = block_first[static_cast<size_t>(bi) + 1];
+    int64_t np = 0;
+    for (int64_t i = r0; i < r1; i++) { np += n - i - 1; }
+    if (np == 0) { return VSG_OK; }
+    std::vector<uint32_t> pq(static_cast<size_t>(np)), pt(static_cast<size_t>(np));
+    int64_t k = 0, cells = 0;
+    for (int64_t i = r0; i < r1; i++) {
+      int64_t tl = 0;
+      for (int64_t j = i + 1; j < n; j++) { pq[static_cast<size_t>(k)] = static_cast<uint32_t>(i); pt[static_cast<size_t>(k)] = static_cast<uint32_t>(j); k++; tl += set->h_len[static_cast<size_t>(j)]; }
+      cells += static_cast<int64_t>(set->h_len[static_cast<size_t>(i)]) * tl;
+    }
+    std::vector<int16_t> sc(static_cast<size_t>(np));
+    std::vector<uint16_t> al(static_cast<size_t>(np)), ma(static_cast<size_t>(np)), mi(static_cast<size_t>(np)), ga(static_cast<size_t>(np));
+    std::vector<int32_t> tr(static_cast<size_t>(np) * 4);
+    int const r = vsg_align_pairs(wc, set, set, np, pq.data(), pt.data(), sc.data(), al.data(), ma.data(), mi.data(), ga.data(),
+                                  tr.data(), nullptr, 0, nullptr);
+    if (r != VSG_OK) { return r; }
+    std::vector<vsg_pair_hit> & o = out[static_cast<size_t>(bi)];
+    k = 0;
+    for (int64_t i = r0; i < r1; i++) {
+      size_t const first = o.size();
+      int const qlen = set->h_len[static_cast<size_t>(i)];
+      for (int64_t j = i + 1; j < n; j++, k++) {
+        if (sc[static_cast<size_t>(k)] == VSG_SCORE_SENTINEL) {
+          Error::set("vsg_allpairs: a pair was deferred to the linear-memory aligner (core/linmemalign.cpp), which this library does not provide");
+          return VSG_EINVAL;
+        }
+        Hit h;
+        std::memset(&h, 0, sizeof h);
+        int const dlen = set->h_len[static_cast<size_t>(j)];
+        h.target = static_cast<int>(j); h.aligned = true;
+        h.shortest = std::min(qlen, dlen); h.longest = std::max(qlen, dlen);
+        h.nwscore = sc[static_cast<size_t>(k)];
+        h.nwalignmentlength = al[static_cast<size_t>(k)];
+        h.nwdiff = al[static_cast<size_t>(k)] - ma[static_cast<size_t>(k)];
+        h.nwgaps = ga[static_cast<size_t>(k)];
+        h.nwindels = al[static_cast<size_t>(k)] - ma[static_cast<size_t>(k)] - mi[static_cast<size_t>(k)];
+        h.matches = al[static_cast<size_t>(k)] - h.nwdiff;
+        h.mismatches = h.nwdiff - h.nwindels;
+        finish_hit(h, &tr[4 * static_cast<size_t>(k)], opts->iddef);
+        if (acceptable_aligned(h, opt_id, opt_weak_id)) {
+          vsg_pair_hit ph;
+          ph.query = static_cast<int32_t>(i); ph.target = h.target; ph.matches = h.matches; ph.mismatches = h.mismatches;
+          ph.gaps = h.nwgaps; ph.alignment_length = h.nwalignmentlength; ph.nwscore = h.nwscore;
+          ph.internal_alignment_length = h.internal_alignmentlength; ph.id = h.id;
+          o.push_back(ph);
+        }
+      }
+      std::sort(o.begin() + static_cast<std::ptrdiff_t>(first), o.end(), [](const vsg_pair_hit & a, const vsg_pair_hit & b) {
+        if (a.id != b.id) { return a.id > b.id; }
+        return a.target < b.target;
+      });
+    }
+    bpairs[static_cast<size_t>(bi)] = np; bcells[static_cast<size_t>(bi)] = cells;
+    return VSG_OK;
+  };
+
+  std::atomic<int64_t> next{0};
+  std::vector<int> rcs(static_cast<size_t>(nthreads), VSG_OK);
+  std::vector<std::string> msgs(static_cast<size_t>(nthreads));
+  auto worker = [&](int t) {
+    vsg_ctx * wc = c->children[static_cast<size_t>(t)];
+    cudaSetDevice(wc->device);
+    for (;;) {
+      int64_t const bi = next.fetch_add(1);
+      if (bi >= nblocks) { break; }
+      int const r = run_block(wc, bi);
+      if (r != VSG_OK) { rcs[static_cast<size_t>(t)] = r; msgs[static_cast<size_t>(t)] = vsg_last_error(); next.store(nblocks); break; }
+    }
+  };
+  if (nthreads == 1) { worker(0); }
+  else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; t++) { pool.emplace_back(worker, t); }
+    for (auto & th : pool) { th.join(); }
+  }
+  for (int t = 0; t < nthreads; t++) {
+    vsg_ctx * wc = c->children[static_cast<size_t>(t)];
+    c->prof_cells += wc->prof_cells; c->prof_fast += wc->prof_fast; c->prof_exact += wc->prof_exact;
+    c->prof_fwd_launches += wc->prof_fwd_launches;
+    c->prof_fwd_ms += wc->prof_fwd_ms; c->prof_tb_ms += wc->prof_tb_ms; c->prof_rank_ms += wc->prof_rank_ms;
+    vsg_profile_reset(wc);
+    if (rcs[static_cast<size_t>(t)] != VSG_OK) { Error::set(msgs[static_cast<size_t>(t)]); return rcs[static_cast<size_t>(t)]; }
+  }
+  int64_t total = 0, tp = 0, tc = 0;
+  for (int64_t bi = 0; bi < nblocks; bi++) { total += static_cast<int64_t>(out[static_cast<size_t>(bi)].size()); tp += bpairs[static_cast<size_t>(bi)]; tc += bcells[static_cast<size_t>(bi)]; }
+  *nhits = total;
+  if (work != nullptr) { work[0] = tp; work[1] = tc; }
+  if (total > cap) { Error::set("vsg_allpairs: hit buffer too small"); return VSG_ECAP; }
+  int64_t pos = 0;
+  for (int64_t bi = 0; bi < nblocks; bi++) {
+    auto const & o = out[static_cast<size_t>(bi)];
+    if (!o.empty()) { std::memcpy(hits + pos, o.data(), sizeof(vsg_pair_hit) * o.size()); pos += static_cast<int64_t>(o.size()); }
+  }
+  return VSG_OK;
+}

@@ -51,6 +51,12 @@ class SearchResult(C.Structure):
                 ("nwscore", C.c_int32), ("id", C.c_double)]
 
 
+class PairHit(C.Structure):
+    _fields_ = [("query", C.c_int32), ("target", C.c_int32), ("matches", C.c_int32), ("mismatches", C.c_int32),
+                ("gaps", C.c_int32), ("alignment_length", C.c_int32), ("nwscore", C.c_int32),
+                ("internal_alignment_length", C.c_int32), ("id", C.c_double)]
+
+
 def declared_symbols() -> List[str]:
     """Every function name include/vsg.h declares."""
     text = open(HEADER).read()
@@ -242,6 +248,21 @@ class Context:
                                        C.byref(opts), res, C.c_int(max_results), _ptr(counts, C.c_int32),
                                        _ptr(work, C.c_int64)), "vsg_search_batch")
         return res, counts, work
+
+
+def allpairs(ctx: "Context", ss: SeqSetHandle, row0: int, nrows: int, opts: SearchOpts, cap: int):
+    """vsg_allpairs -> (numpy structured array of hits, work[2])"""
+    dt = np.dtype([("query", np.int32), ("target", np.int32), ("matches", np.int32), ("mismatches", np.int32),
+                   ("gaps", np.int32), ("alignment_length", np.int32), ("nwscore", np.int32),
+                   ("internal_alignment_length", np.int32), ("id", np.float64)])
+    assert dt.itemsize == C.sizeof(PairHit)
+    hits = np.zeros(cap, dtype=dt)
+    n = C.c_int64()
+    work = np.zeros(2, dtype=np.int64)
+    _check(load().vsg_allpairs(ctx.h, ss.h, C.c_int64(row0), C.c_int64(nrows), C.byref(opts),
+                               hits.ctypes.data_as(C.POINTER(PairHit)), C.c_int64(cap), C.byref(n),
+                               _ptr(work, C.c_int64)), "vsg_allpairs")
+    return hits[: n.value], work
 
 
 def default_search_opts() -> SearchOpts:
