@@ -139,6 +139,118 @@ def reference_arm(args, rank):
     print(json.dumps(line))
 
 
+def allpairs_workload(args, rank, world, local):
+    """configs[4] shape: --allpairs_global on 200 000 reads x 400 nt (2 000 roots, 15 % divergence),
+    --id 0.7.  One step = `rows` query rows per GPU against all later reads (the full run would be
+    3.2e15 cells; SURVEY.md §8d prescribes a stated prefix).  Rows shard across GPUs, no collective."""
+    from vsearch_b200 import synth
+    N_READS, L, ROOTS, DIVA, SEEDA, IDA = 200_000, 400, 2000, 0.15, 5, 0.7
+    rng = np.random.default_rng(SEEDA)
+    roots = synth.random_seqs(rng, ROOTS, L)
+    reads = synth.mutate_batch(rng, roots[rng.integers(0, ROOTS, size=N_READS)], DIVA)
+    nsteps = args.warmup + args.steps
+    cfg = {"workload": "allpairs_global 200k x 400nt reads, id 0.7 (configs[4]), prefix of query rows",
+           "masking": "none", "l2": "direction blocks of one step (> 100 GB streamed) exceed the 126 MB L2"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import checkers
+        cores = os.cpu_count() or 1
+        if checkers.ref() is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvsref.so not built"}))
+            return
+        lib = checkers.ref(); lib.vsref_allpairs_rows.restype = C.c_longlong
+        if args.ref_rows <= 0:
+            args.ref_rows = max(1, cores // 8)   # ~10-15 s of CPU work per step
+        r = checkers.RefDb(reads, id=IDA, dust=0)
+        tot_t = 0.0; tot_c = 0; tot_p = 0
+        for step in range(nsteps):
+            lib.vsref_work_reset()
+            t0 = time.perf_counter()
+            lib.vsref_allpairs_rows(C.c_void_p(r.h), C.c_int(step * args.ref_rows), C.c_int(args.ref_rows), C.c_int(cores))
+            dt = time.perf_counter() - t0
+            p = C.c_longlong(); c = C.c_longlong(); k = C.c_longlong()
+            lib.vsref_work_get(C.byref(p), C.byref(c), C.byref(k))
+            if step >= args.warmup:
+                tot_t += dt; tot_c += c.value; tot_p += p.value
+        r.close()
+        g = tot_c / tot_t / 1e9
+        cfg["rows_per_step"] = args.ref_rows
+        print(json.dumps({"impl": "reference", "metric": "allpairs_global_gcups", "value": g, "unit": "GCUPS",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "int16", "data": "synthetic", "config": cfg,
+                          "pairs_per_s": tot_p / tot_t,
+                          "cpu_baseline": {"value": g, "unit": "GCUPS", "cores": cores, "kind": "reference",
+                                           "sample": f"{args.ref_rows} query rows per step, search16 on {cores} threads"},
+                          "e2e": {"value": g, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    import torch.distributed as dist
+    from vsearch_b200 import lib as vlib
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = vlib.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local))
+    if world > 1:   # rank 0's packed reads go to every GPU over NCCL
+        d_cat = torch.empty(reads.cat.shape[0], dtype=torch.uint8, device="cuda")
+        d_off = torch.empty(N_READS, dtype=torch.int64, device="cuda")
+        d_len = torch.empty(N_READS, dtype=torch.int32, device="cuda")
+        if rank == 0:
+            d_cat.copy_(torch.from_numpy(reads.cat)); d_off.copy_(torch.from_numpy(reads.offs)); d_len.copy_(torch.from_numpy(reads.lens))
+        for t in (d_cat, d_off, d_len):
+            dist.broadcast(t, 0)
+        torch.cuda.synchronize()
+        ss = ctx.seqset_from_device(d_cat.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), N_READS)
+    else:
+        ss = ctx.seqset(reads)
+    o = vlib.default_search_opts(); o.id = IDA
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    work = np.zeros(2, dtype=np.int64); nh = 0; sampler = None; l0 = 0
+    for step in range(nsteps):
+        if step == args.warmup:
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            sampler = ClockSampler(local); sampler.start(); ctx.profile_reset(); l0 = vlib.launch_count()
+            ev0.record(stream)
+        row0 = (step * world + rank) * args.rows
+        hits, w = vlib.allpairs(ctx, ss, row0, args.rows, o, args.rows * N_READS)
+        if step >= args.warmup:
+            work += w; nh += len(hits)
+    ev1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.summary(); prof = ctx.profile(); launches = vlib.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        wt = torch.tensor(work, dtype=torch.int64, device="cuda"); dist.all_reduce(wt, op=dist.ReduceOp.SUM); work = wt.cpu().numpy()
+    if rank == 0:
+        g = work[1] / (ms * 1e-3) / 1e9
+        peak_ops = ctx.int_peak()
+        cfg.update({"rows_per_step_per_gpu": args.rows, "parallelism": f"query rows sharded x{world}, reads NCCL-broadcast"})
+        print(json.dumps({"metric": "allpairs_global_gcups", "value": g, "unit": "GCUPS", "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
+                          "data": "synthetic", "config": cfg, "pairs_per_s": float(work[0]) / (ms * 1e-3),
+                          "hits_per_step": nh / args.steps,
+                          "e2e": {"value": g, "unit": "GCUPS", "h2d_bytes_per_step": 16,
+                                  "d2h_bytes_per_step": int(48 * nh / max(1, args.steps)),
+                                  "note": "reads resident; per step only the row range goes up and the hit table comes back (included)"},
+                          "gpu_launches": int(launches), "clocks": clocks,
+                          "roofline": {"bound": "int_alu", "kernel": "nw_fast_kernel<13,false>",
+                                       "achieved_in_step_overlapping_streams": prof.cells / max(1e-9, prof.fwd_ms * 1e-3) / 1e9,
+                                       "peak": 2.0 * peak_ops / 15.0 / 1e9, "unit": "GCUPS", "frac": g / (2.0 * peak_ops / 15.0 / 1e9),
+                                       "note": "frac uses whole-step throughput (forward + traceback + host) against the forward-kernel peak"}}))
+    ss.close(); ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -149,6 +261,11 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=8192, help="queries per step of the reference arm")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="queries of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="usearch", choices=["usearch", "allpairs"],
+                    help="usearch = configs[1] (default, the headline); allpairs = configs[4] shape (dense N^2 DP)")
+    ap.add_argument("--rows", type=int, default=32, help="allpairs: query rows per step per GPU")
+    ap.add_argument("--ref-rows", type=int, default=0,
+                    help="allpairs: query rows per step of the reference arm (0 = one per host thread)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -157,6 +274,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
+    if args.workload == "allpairs":
+        allpairs_workload(args, rank, world, local)
+        return
     if args.impl == "reference":
         reference_arm(args, rank)
         return

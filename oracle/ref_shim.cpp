@@ -25,6 +25,7 @@
 #include <string>
 #include <vector>
 #include <memory>
+#include <thread>
 
 /* Link-time instrumentation of the UNMODIFIED reference: oracle/Makefile links libvsref.so with
    -Wl,--wrap=<search16>, so every call the reference makes to search16 lands here first.  We only
@@ -273,6 +274,47 @@ int vsref_db_search_batch(void * h, int nq, const char * qcat, const int64_t * q
     hits += counts[static_cast<size_t>(q)] > 0;
   }
   return hits;
+}
+
+/* the per-query body of allpairs_thread_run (commands/allpairs_global.cpp:395-431) for rows
+   [row0, row0+nrows) of the session's database on `threads` host threads: search16_qprep + ONE
+   search16 call against all later sequences.  Exists to TIME the reference's aligner on the dense
+   all-pairs workload (results are discarded; the --wrap counter records pairs and cells). */
+long long vsref_allpairs_rows(void * h, int row0, int nrows, int threads)
+{
+  RefDb * r = static_cast<RefDb *>(h);
+  Database & db = r->db;
+  Parameters const & p = r->params;
+  int const n = static_cast<int>(db.getsequencecount());
+  std::atomic<int> next{row0};
+  std::atomic<long long> pairs{0};
+  auto worker = [&]() {
+    s16info_s * s = search16_init(p.opt_match, p.opt_mismatch, p.opt_gap_open_query_left, p.opt_gap_open_target_left,
+                                  p.opt_gap_open_query_interior, p.opt_gap_open_target_interior,
+                                  p.opt_gap_open_query_right, p.opt_gap_open_target_right,
+                                  p.opt_gap_extension_query_left, p.opt_gap_extension_target_left,
+                                  p.opt_gap_extension_query_interior, p.opt_gap_extension_target_interior,
+                                  p.opt_gap_extension_query_right, p.opt_gap_extension_target_right, p.opt_n_mismatch);
+    std::vector<unsigned int> seqnos;
+    std::vector<CELL> sc; std::vector<unsigned short> a, m, mm, g; std::vector<char *> cg;
+    for (;;) {
+      int const i = next.fetch_add(1);
+      if (i >= row0 + nrows || i >= n) { break; }
+      int const cnt = n - i - 1;
+      if (cnt <= 0) { continue; }
+      seqnos.resize(cnt); sc.resize(cnt); a.resize(cnt); m.resize(cnt); mm.resize(cnt); g.resize(cnt); cg.assign(cnt, nullptr);
+      for (int j = 0; j < cnt; j++) { seqnos[j] = static_cast<unsigned int>(i + 1 + j); }
+      search16_qprep(s, db.mutatesequence(i), static_cast<int>(db.getsequencelen(i)));
+      search16(s, static_cast<unsigned int>(cnt), seqnos.data(), sc.data(), a.data(), m.data(), mm.data(), g.data(), cg.data(), db);
+      for (int j = 0; j < cnt; j++) { if (cg[j] != nullptr) { xfree(cg[j]); } }
+      pairs += cnt;
+    }
+    search16_exit(s);
+  };
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; t++) { pool.emplace_back(worker); }
+  for (auto & th : pool) { th.join(); }
+  return pairs.load();
 }
 
 }  // extern "C"

@@ -440,7 +440,7 @@ extern "C" int vsg_allpairs(vsg_ctx * c, const vsg_seqset * set, int64_t row0, i
     block_first.push_back(row0 + nrows);
   }
   int64_t const nblocks = static_cast<int64_t>(block_first.size()) - 1;
-  int nthreads = 4;
+  int nthreads = 8;
   if (const char * e = std::getenv("VSG_HOST_THREADS")) { nthreads = std::max(1, std::atoi(e)); }
   nthreads = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nthreads, nblocks)));
   while (static_cast<int>(c->children.size()) < nthreads) {
