@@ -59,6 +59,18 @@ void vsg_ctx_destroy(vsg_ctx * ctx);
 void * vsg_ctx_stream(vsg_ctx * ctx);
 int vsg_ctx_sync(vsg_ctx * ctx);
 
+/* ---- pairs the 16-bit aligner cannot take (score == VSG_SCORE_SENTINEL): the reference re-aligns
+ *      them with its scalar LinearMemoryAligner (core/searchcore.cpp:806-832,
+ *      commands/allpairs_global.cpp:447-473).  That routine stays on the host side of the boundary:
+ *      the embedding application registers it here and vsg_search_batch / vsg_allpairs call it for
+ *      exactly those pairs.  query/target are indices into the sequence sets of the call, strand is
+ *      1 when the query is to be reverse-complemented.  out[9] = {nwscore, alignment length,
+ *      matches, mismatches, gaps, trim_q_left, trim_t_left, trim_q_right, trim_t_right} (trims as in
+ *      vsg_align_pairs).  Return 0 on success.  Called from the library's worker threads, possibly
+ *      concurrently.  Without a callback such a pair makes the call fail with VSG_EINVAL. ---- */
+typedef int (*vsg_fallback_fn)(void * user, int64_t query, int32_t strand, int64_t target, int64_t * out);
+int vsg_ctx_set_fallback(vsg_ctx * ctx, vsg_fallback_fn fn, void * user);
+
 /* ---- sequences: replaces Database::add / getsequence / getsequencelen
  *      (core/db.hpp:137-201, core/db.cpp:170-226).  ASCII, one byte per nucleotide, any case,
  *      IUPAC allowed; offsets index into `cat`. `host` selects where cat/off/len live

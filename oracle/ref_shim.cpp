@@ -19,6 +19,8 @@
 #include "core/minheap.hpp"
 #include "core/unique.hpp"
 #include "core/mask.hpp"
+#include "core/linmemalign.hpp"
+#include "utils/string_alloc.hpp"
 
 #include <cstring>
 #include <cstdlib>
@@ -274,6 +276,25 @@ int vsref_db_search_batch(void * h, int nq, const char * qcat, const int64_t * q
     hits += counts[static_cast<size_t>(q)] > 0;
   }
   return hits;
+}
+
+/* LinearMemoryAligner::align + alignstats (core/linmemalign.cpp) with the session's scoring: the
+   reference's answer for pairs its 16-bit aligner defers.  out = {score, alnlen, matches,
+   mismatches, gaps}; the CIGAR goes to cigar (cap bytes). */
+int vsref_lma(void * h, const char * q, int qlen, const char * t, int tlen, long long * out, char * cigar, int cap)
+{
+  RefDb * r = static_cast<RefDb *>(h);
+  struct Scoring scoring = scoring_from_options(r->params);
+  LinearMemoryAligner lma(scoring);
+  std::string qs(q, static_cast<size_t>(qlen)), ts(t, static_cast<size_t>(tlen));
+  char * c = xstrdup(lma.align(qs.c_str(), ts.c_str(), qlen, tlen));
+  int64_t sc = 0, al = 0, ma = 0, mi = 0, ga = 0;
+  lma.alignstats(c, qs.c_str(), ts.c_str(), &sc, &al, &ma, &mi, &ga);
+  out[0] = sc; out[1] = al; out[2] = ma; out[3] = mi; out[4] = ga;
+  int rc = 0;
+  if (static_cast<int>(std::strlen(c)) + 1 > cap) { rc = -1; } else { std::strcpy(cigar, c); }
+  xfree(c);
+  return rc;
 }
 
 /* the per-query body of allpairs_thread_run (commands/allpairs_global.cpp:395-431) for rows

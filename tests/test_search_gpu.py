@@ -140,3 +140,72 @@ def test_search_vs_compiled_reference(ctx):
         hit += bool(got) and got[0][0] == int(src[i])
     assert hit > 100
     ix.close(); db.close(); qs.close()
+
+
+@pytest.mark.skipif(checkers.ref() is None, reason="oracle/_ref/libvsref.so not present")
+def test_deferred_pairs_go_through_the_fallback_callback(ctx):
+    """pairs the 16-bit aligner cannot take (q*d > 25e6) are resolved by the host application's
+    linear-memory aligner through vsg_ctx_set_fallback — here the reference's own LinearMemoryAligner —
+    and the hit table still equals the reference's"""
+    import ctypes as C
+    import re
+    rng = np.random.default_rng(41)
+    big = synth.random_seqs(rng, 3, 5200)
+    small = synth.random_seqs(rng, 30, 400)
+    dbs = synth.SeqSet([big[i].tobytes() for i in range(3)] + [small[i].tobytes() for i in range(30)])
+    queries = [synth.mutate(rng, big[0], 0.03).tobytes(),            # 5200 x 5200 > 25e6 -> deferred
+               synth.mutate(rng, big[1][:5100], 0.05).tobytes(),
+               synth.mutate(rng, small[3], 0.05).tobytes(),          # ordinary
+               synth.mutate(rng, small[7], 0.02).tobytes()]
+    qss = synth.SeqSet(queries)
+    r = checkers.RefDb(dbs, id=0.8, maxaccepts=2, maxrejects=8)
+    want = r.search(qss, max_results=r.tophits)
+    th = r.tophits
+    rlib = checkers.ref()
+
+    def fallback(q, strand, t):
+        assert strand == 0
+        out = (C.c_longlong * 5)()
+        qs_, ts_ = queries[q], dbs.seq(t)
+        buf = C.create_string_buffer(len(qs_) + len(ts_) + 8)
+        assert rlib.vsref_lma(C.c_void_p(r.h), qs_, C.c_int(len(qs_)), ts_, C.c_int(len(ts_)), out, buf, C.c_int(len(buf))) == 0
+        ops = re.findall(r"(\d*)([MID])", buf.value.decode())
+        f, l = ops[0], ops[-1]
+        fr = int(f[0]) if f[0] else 1; lr = int(l[0]) if l[0] else 1
+        return [out[0], out[1], out[2], out[3], out[4], fr if f[1] == "D" else 0, fr if f[1] == "I" else 0,
+                lr if l[1] == "D" else 0, lr if l[1] == "I" else 0]
+
+    db = ctx.seqset(dbs); qs = ctx.seqset(qss)
+    ix = ctx.index(db, 8, 0)
+    o = gpu_opts(0.8, 2, 8)
+    with pytest.raises(vlib.VsgError, match="linear-memory aligner"):
+        ctx.search(ix, db, qs, 0, len(queries), o, th)
+    ctx.set_fallback(fallback)
+    res, counts, _ = ctx.search(ix, db, qs, 0, len(queries), o, th)
+    for i in range(len(queries)):
+        assert rows_of(res, counts, i, th) == [list(t) for t in want[i]], i
+    assert counts[0] >= 1 and rows_of(res, counts, 0, th)[0][0] == 0
+    load = vlib.load(); load.vsg_ctx_set_fallback(ctx.h, None, None)
+    r.close(); ix.close(); db.close(); qs.close()
+
+
+def test_long_queries_rank_vs_oracle(ctx):
+    """queries with more than 2048 k-mer windows take the HBM de-duplication path of the ranker"""
+    rng = np.random.default_rng(43)
+    roots = synth.random_seqs(rng, 30, 700)
+    dbs = synth.SeqSet([synth.mutate(rng, roots[i % 30], 0.05).tobytes() for i in range(400)])
+    queries = [b"".join(roots[j].tobytes() for j in range(4)),                 # 2800 nt
+               (roots[5].tobytes() + roots[6].tobytes()) * 4,                   # 5600 nt, every k-mer 4 times
+               synth.random_seqs(rng, 1, 2056)[0].tobytes(),                    # just past the shared-memory capacity
+               synth.random_seqs(rng, 1, 2055)[0].tobytes(),                    # exactly at it
+               roots[9].tobytes()]
+    qss = synth.SeqSet(queries)
+    db = ctx.seqset(dbs); qs = ctx.seqset(qss)
+    ix = ctx.index(db, 8, 0)
+    od = checkers.OracleDb(dbs)
+    opts = checkers.search_opts(len(dbs), id=0.9, maxaccepts=4, maxrejects=16)
+    seqno, count, nc = ctx.rank(ix, qs, 0, len(queries), opts.minwordmatches, opts.tophits)
+    for i, q in enumerate(queries):
+        s, c = od.topscores(q, opts)
+        assert seqno[i, :nc[i]].tolist() == s.tolist() and count[i, :nc[i]].tolist() == c.tolist(), i
+    od.close(); ix.close(); db.close(); qs.close()

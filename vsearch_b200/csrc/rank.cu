@@ -146,6 +146,7 @@ __device__ __forceinline__ int next_pow2(int v)
 __device__ __forceinline__ uint64_t make_key(uint32_t count, uint32_t len, uint32_t seqno)
 {
   uint32_t const l = len > 0x1ffffffu ? 0x1ffffffu : len;
+  if (count > 32767u) { count = 32767u; }  // the reference saturates its counters (searchcore.cpp:306-315)
   return (static_cast<uint64_t>(count) << 49) | (static_cast<uint64_t>(0x1ffffffu - l) << 24) |
          static_cast<uint64_t>(0xffffffu - seqno);
 }
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(RANK_THREADS)
 rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restrict__ shards, int nshards,
             int k, int mask_lower, int minwordmatches, int tophits,
             uint32_t * __restrict__ out_seqno, uint32_t * __restrict__ out_count, int32_t * __restrict__ out_n,
-            int32_t * __restrict__ status)
+            int32_t * __restrict__ status, uint32_t * __restrict__ scratch, size_t scratch_stride, int bitmap_words)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   uint64_t * const cand = reinterpret_cast<uint64_t *>(smem);                     // CAND_CAP
@@ -174,33 +175,58 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
     int const len = qs.len[q];
     int const nwin = len - k + 1;
     if (threadIdx.x == 0) { s_ncand = 0; s_nk = 0; }
-    if (nwin > KMER_CAP) {
+    bool const longq = nwin > KMER_CAP;
+    if (longq && (scratch == nullptr || nwin > 65535)) {
       if (threadIdx.x == 0) { out_n[qi] = 0; atomicExch(status, 1); }
       continue;
     }
-    // 1. the query's k-mers, sorted, duplicates and masked windows invalidated (0xffffffff)
-    int const np2 = next_pow2(nwin > 1 ? nwin : 1);
-    for (int i = threadIdx.x; i < np2; i += blockDim.x) {
-      uint32_t km = 0xffffffffu;
-      if (i < nwin) {
-        uint32_t v;
-        if (kmer_at(s, i + k - 1, k, mask_lower, v)) { km = v; }
+    int np2, nk, nchunks = 1;
+    uint32_t * gk = nullptr;
+    if (!longq) {
+      // 1. the query's k-mers, sorted, duplicates and masked windows invalidated (0xffffffff)
+      np2 = next_pow2(nwin > 1 ? nwin : 1);
+      for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+        uint32_t km = 0xffffffffu;
+        if (i < nwin) {
+          uint32_t v;
+          if (kmer_at(s, i + k - 1, k, mask_lower, v)) { km = v; }
+        }
+        kmers[i] = km;
       }
-      kmers[i] = km;
+      bitonic_sort_shared<uint32_t, false>(kmers, np2);
+      int mine = 0;
+      for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+        uint32_t const v = kmers[i];
+        bool const keep = (v != 0xffffffffu) && (i == 0 || kmers[i - 1] != v);
+        lbeg[i] = keep ? 1u : 0u;  // temporary keep flag
+        mine += keep;
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < np2; i += blockDim.x) { if (lbeg[i] == 0u) { kmers[i] = 0xffffffffu; } }
+      atomicAdd(&s_nk, mine);
+      __syncthreads();
+      nk = s_nk;
+    } else {
+      // 1'. long query: de-duplicate through a 4^k-bit map in this CTA's HBM scratch, collect the
+      //     distinct k-mers in a list there, and feed them through shared memory KMER_CAP at a time
+      uint32_t * const bm = scratch + static_cast<size_t>(blockIdx.x) * scratch_stride;
+      gk = bm + bitmap_words;
+      for (int i = threadIdx.x; i < bitmap_words; i += blockDim.x) { bm[i] = 0; }
+      __syncthreads();
+      for (int p = threadIdx.x; p < nwin; p += blockDim.x) {
+        uint32_t v;
+        if (kmer_at(s, p + k - 1, k, mask_lower, v)) {
+          uint32_t const bit = 1u << (v & 31);
+          uint32_t const old = atomicOr(&bm[v >> 5], bit);
+          if ((old & bit) == 0) { gk[atomicAdd(&s_nk, 1)] = v; }
+        }
+      }
+      __threadfence_block();
+      __syncthreads();
+      nk = s_nk;
+      nchunks = nk > 0 ? (nk + KMER_CAP - 1) / KMER_CAP : 1;
+      np2 = 1;
     }
-    bitonic_sort_shared<uint32_t, false>(kmers, np2);
-    int mine = 0;
-    for (int i = threadIdx.x; i < np2; i += blockDim.x) {
-      uint32_t const v = kmers[i];
-      bool const keep = (v != 0xffffffffu) && (i == 0 || kmers[i - 1] != v);
-      lbeg[i] = keep ? 1u : 0u;  // temporary keep flag
-      mine += keep;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < np2; i += blockDim.x) { if (lbeg[i] == 0u) { kmers[i] = 0xffffffffu; } }
-    atomicAdd(&s_nk, mine);
-    __syncthreads();
-    int const nk = s_nk;
     // search_topscores: count >= min(minwordmatches, kmersamplecount)  (searchcore.cpp:320)
     uint32_t const minmatches = static_cast<uint32_t>(minwordmatches < nk ? minwordmatches : nk);
 
@@ -208,6 +234,13 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
       ShardDev const S = shards[sh];
       // 2. zero the counters; fetch the bounds of every k-mer's posting list in this shard
       for (int i = threadIdx.x; i < COUNTER_WORDS; i += blockDim.x) { counters[i] = 0; }
+      for (int chunk = 0; chunk < nchunks; chunk++) {
+      if (longq) {
+        int const cn = nk > 0 ? min(KMER_CAP, nk - chunk * KMER_CAP) : 1;
+        for (int i = threadIdx.x; i < cn; i += blockDim.x) { kmers[i] = nk > 0 ? gk[chunk * KMER_CAP + i] : 0xffffffffu; }
+        np2 = cn;
+        __syncthreads();
+      }
       for (int i = threadIdx.x; i < np2; i += blockDim.x) {
         uint32_t const km = kmers[i];
         uint32_t b = 0, n = 0;
@@ -273,6 +306,7 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
         }
       }
       __syncthreads();
+      }  // chunk
       // 4. threshold scan.  Common case: count the survivors, one block-wide prefix sum, write them
       //    straight to their slots (no barrier per segment).  Only if they would not fit does the
       //    segmented sort-and-cut path below run.
@@ -347,7 +381,7 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
     //    count T of the tophits-th best with a histogram, keep count >= T, sort only those.
     int m = s_ncand;
     __syncthreads();
-    if (m > 2 * tophits) {
+    if (m > 2 * tophits && nk + 1 <= 2 * KMER_CAP) {
       uint32_t * const hist = lbeg;  // 2 * KMER_CAP words available, counts are <= nk <= KMER_CAP
       int const nb = nk + 1;
       for (int i = threadIdx.x; i < nb; i += blockDim.x) { hist[i] = 0; }
@@ -533,11 +567,22 @@ int rank_enqueue(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * queries, 
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
   int const grid = static_cast<int>(std::min<int64_t>(nq, static_cast<int64_t>(sms) * 2));
+  // queries with more than KMER_CAP windows de-duplicate their k-mers in HBM scratch
+  int maxlen = 0;
+  for (int64_t q = q0; q < q0 + nq; q++) { maxlen = std::max(maxlen, queries->h_len[static_cast<size_t>(q)]); }
+  uint32_t * d_scratch = nullptr;
+  size_t stride = 0;
+  int const bitmap_words = std::max(1, (1 << (2 * ix->k)) >> 5);
+  if (maxlen - ix->k + 1 > KMER_CAP) {
+    stride = static_cast<size_t>(bitmap_words) + static_cast<size_t>(maxlen) + 8;
+    if ((rc = c->rank_scratch.reserve(sizeof(uint32_t) * stride * static_cast<size_t>(grid))) != VSG_OK) { return rc; }
+    d_scratch = static_cast<uint32_t *>(c->rank_scratch.p);
+  }
   VSG_CUDA_OK(cudaEventRecord(c->ev[4], rs));
   rank_kernel<<<grid, RANK_THREADS, RANK_SMEM, rs>>>(
       queries->d, q0, static_cast<int>(nq), ix->db->d, static_cast<const ShardDev *>(ix->b_shards.p),
       static_cast<int>(ix->h_shards.size()), ix->k, mask_lower, minwordmatches, tophits, *d_seqno, *d_count, *d_n,
-      *d_status);
+      *d_status, d_scratch, stride, bitmap_words);
   count_launch();
   VSG_CUDA_OK(cudaEventRecord(c->ev[5], rs));
   if (use_hi) { VSG_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev[5], 0)); }
@@ -580,7 +625,7 @@ extern "C" int vsg_rank(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * qu
   VSG_CUDA_OK(cudaGetLastError());
   rank_collect_time(c);
   if (status != 0) {
-    Error::set("vsg_rank: a query is longer than the device ranker supports (2047 + wordlength nt)");
+    Error::set("vsg_rank: a query is longer than the device ranker supports (65 534 + wordlength nt)");
     return VSG_EINVAL;
   }
   return VSG_OK;

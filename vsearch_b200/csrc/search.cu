@@ -165,6 +165,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
     c->children[static_cast<size_t>(t)]->fast_disabled = c->fast_disabled;
   }
 
+  vsg_ctx * const parent = c;
   auto run_batch = [&](vsg_ctx * c, int64_t b0, int64_t & total_pairs, int64_t & total_cells) -> int {
   std::vector<uint32_t> h_seqno, h_count;
   std::vector<int32_t> h_n;
@@ -210,7 +211,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
       rank_collect_time(c);
       if (status != 0) {
         if (rc_set) { vsg_seqset_destroy(rc_set); }
-        Error::set("vsg_search_batch: a query is longer than the device ranker supports (2047 + wordlength nt)");
+        Error::set("vsg_search_batch: a query is longer than the device ranker supports (65 534 + wordlength nt)");
         return VSG_EINVAL;
       }
     }
@@ -308,24 +309,36 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
           if (S.rejects < maxrejects && S.accepts < maxaccepts) {
             Hit & h = hits[static_cast<size_t>(S.hit_base) + x];
             if (h.rejected) { S.rejects++; continue; }
-            if (a_score[i] == VSG_SCORE_SENTINEL) {
-              if (rc_set) { vsg_seqset_destroy(rc_set); }
-              Error::set("vsg_search_batch: a pair was deferred to the linear-memory aligner "
-                         "(core/linmemalign.cpp), which this library does not provide");
-              return VSG_EINVAL;
+            int64_t fb[9];
+            bool const diverted = (a_score[i] == VSG_SCORE_SENTINEL);
+            if (diverted) {
+              // the reference's LinearMemoryAligner path (searchcore.cpp:806-832), host side of the boundary
+              if (parent->fallback == nullptr ||
+                  parent->fallback(parent->fallback_user, q0 + b0 + ql, strand, h.target, fb) != 0) {
+                if (rc_set) { vsg_seqset_destroy(rc_set); }
+                Error::set("vsg_search_batch: a pair was deferred to the linear-memory aligner (core/linmemalign.cpp) "
+                           "and no vsg_ctx_set_fallback callback resolved it");
+                return VSG_EINVAL;
+              }
             }
             int const dlen = db->h_len[static_cast<size_t>(h.target)];
             h.aligned = true;
             h.shortest = std::min(qlen, dlen);
             h.longest = std::max(qlen, dlen);
+            int32_t trims4[4] = {a_tr[4 * i], a_tr[4 * i + 1], a_tr[4 * i + 2], a_tr[4 * i + 3]};
+            int64_t nal = a_al[i], nma = a_ma[i], nmi = a_mi[i], nga = a_ga[i];
             h.nwscore = a_score[i];
-            h.nwalignmentlength = a_al[i];
-            h.nwdiff = a_al[i] - a_ma[i];
-            h.nwgaps = a_ga[i];
-            h.nwindels = a_al[i] - a_ma[i] - a_mi[i];
-            h.matches = a_al[i] - h.nwdiff;
+            if (diverted) {
+              h.nwscore = static_cast<int>(fb[0]); nal = fb[1]; nma = fb[2]; nmi = fb[3]; nga = fb[4];
+              for (int z = 0; z < 4; z++) { trims4[z] = static_cast<int32_t>(fb[5 + z]); }
+            }
+            h.nwalignmentlength = static_cast<int>(nal);
+            h.nwdiff = static_cast<int>(nal - nma);
+            h.nwgaps = static_cast<int>(nga);
+            h.nwindels = static_cast<int>(nal - nma - nmi);
+            h.matches = static_cast<int>(nal) - h.nwdiff;
             h.mismatches = h.nwdiff - h.nwindels;
-            finish_hit(h, &a_tr[4 * i], opts->iddef);
+            finish_hit(h, trims4, opts->iddef);
             if (acceptable_aligned(h, opt_id, opt_weak_id)) { S.accepts++; } else { S.rejects++; }
             ++i;
           }
@@ -480,8 +493,11 @@ extern "C" int vsg_allpairs(vsg_ctx * c, const vsg_seqset * set, int64_t row0, i
       size_t const first = o.size();
       int const qlen = set->h_len[static_cast<size_t>(i)];
       for (int64_t j = i + 1; j < n; j++, k++) {
-        if (sc[static_cast<size_t>(k)] == VSG_SCORE_SENTINEL) {
-          Error::set("vsg_allpairs: a pair was deferred to the linear-memory aligner (core/linmemalign.cpp), which this library does not provide");
+        int64_t fb[9];
+        bool const diverted = (sc[static_cast<size_t>(k)] == VSG_SCORE_SENTINEL);
+        if (diverted && (c->fallback == nullptr || c->fallback(c->fallback_user, i, 0, j, fb) != 0)) {
+          Error::set("vsg_allpairs: a pair was deferred to the linear-memory aligner (core/linmemalign.cpp) "
+                     "and no vsg_ctx_set_fallback callback resolved it");
           return VSG_EINVAL;
         }
         Hit h;
@@ -489,14 +505,20 @@ extern "C" int vsg_allpairs(vsg_ctx * c, const vsg_seqset * set, int64_t row0, i
         int const dlen = set->h_len[static_cast<size_t>(j)];
         h.target = static_cast<int>(j); h.aligned = true;
         h.shortest = std::min(qlen, dlen); h.longest = std::max(qlen, dlen);
+        int32_t trims4[4] = {tr[4 * static_cast<size_t>(k)], tr[4 * static_cast<size_t>(k) + 1], tr[4 * static_cast<size_t>(k) + 2], tr[4 * static_cast<size_t>(k) + 3]};
+        int64_t nal = al[static_cast<size_t>(k)], nma = ma[static_cast<size_t>(k)], nmi = mi[static_cast<size_t>(k)], nga = ga[static_cast<size_t>(k)];
         h.nwscore = sc[static_cast<size_t>(k)];
-        h.nwalignmentlength = al[static_cast<size_t>(k)];
-        h.nwdiff = al[static_cast<size_t>(k)] - ma[static_cast<size_t>(k)];
-        h.nwgaps = ga[static_cast<size_t>(k)];
-        h.nwindels = al[static_cast<size_t>(k)] - ma[static_cast<size_t>(k)] - mi[static_cast<size_t>(k)];
-        h.matches = al[static_cast<size_t>(k)] - h.nwdiff;
+        if (diverted) {
+          h.nwscore = static_cast<int>(fb[0]); nal = fb[1]; nma = fb[2]; nmi = fb[3]; nga = fb[4];
+          for (int z = 0; z < 4; z++) { trims4[z] = static_cast<int32_t>(fb[5 + z]); }
+        }
+        h.nwalignmentlength = static_cast<int>(nal);
+        h.nwdiff = static_cast<int>(nal - nma);
+        h.nwgaps = static_cast<int>(nga);
+        h.nwindels = static_cast<int>(nal - nma - nmi);
+        h.matches = static_cast<int>(nal) - h.nwdiff;
         h.mismatches = h.nwdiff - h.nwindels;
-        finish_hit(h, &tr[4 * static_cast<size_t>(k)], opts->iddef);
+        finish_hit(h, trims4, opts->iddef);
         if (acceptable_aligned(h, opt_id, opt_weak_id)) {
           vsg_pair_hit ph;
           ph.query = static_cast<int32_t>(i); ph.target = h.target; ph.matches = h.matches; ph.mismatches = h.mismatches;

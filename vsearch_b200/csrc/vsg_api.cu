@@ -246,7 +246,7 @@ extern "C" void vsg_ctx_destroy(vsg_ctx * c)
   if (c->stream != nullptr) { cudaStreamSynchronize(c->stream); }
   for (DevBuf * b : {&c->dir, &c->bnd, &c->he, &c->cigar_scratch, &c->cigar_dense, &c->stats,
                      &c->tasks_fast, &c->tasks_exact, &c->pairs, &c->cigar_len, &c->cigar_offs,
-                     &c->cub_tmp, &c->rank_tmp}) { b->release(); }
+                     &c->cub_tmp, &c->rank_tmp, &c->rank_scratch}) { b->release(); }
   for (PinBuf * b : {&c->h_tasks, &c->h_stats, &c->h_pairs, &c->h_misc}) { b->release(); }
   for (auto & ev : c->ev) { if (ev != nullptr) { cudaEventDestroy(ev); } }
   for (auto & ev : c->ev_pool) { cudaEventDestroy(ev); }
@@ -254,6 +254,14 @@ extern "C" void vsg_ctx_destroy(vsg_ctx * c)
   if (c->ev_hi != nullptr) { cudaEventDestroy(c->ev_hi); }
   if (c->stream != nullptr) { cudaStreamDestroy(c->stream); }
   delete c;
+}
+
+extern "C" int vsg_ctx_set_fallback(vsg_ctx * c, vsg_fallback_fn fn, void * user)
+{
+  if (c == nullptr) { return VSG_EINVAL; }
+  c->fallback = fn;
+  c->fallback_user = user;
+  return VSG_OK;
 }
 
 extern "C" void * vsg_ctx_stream(vsg_ctx * c) { return c != nullptr ? static_cast<void *>(c->stream) : nullptr; }

@@ -118,7 +118,7 @@ struct vsg_ctx {
   bool fast_disabled = false;  // VSG_DISABLE_FAST=1 (tests force the exact kernel)
   // scratch
   vsg::DevBuf dir, bnd, he, cigar_scratch, cigar_dense, stats, tasks_fast, tasks_exact, pairs,
-      cigar_len, cigar_offs, cub_tmp, rank_tmp;
+      cigar_len, cigar_offs, cub_tmp, rank_tmp, rank_scratch;
   vsg::PinBuf h_tasks, h_stats, h_pairs, h_misc;
   size_t dir_budget = (size_t)64 << 30;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -127,5 +127,7 @@ struct vsg_ctx {
   float prof_fwd_ms = 0.f, prof_tb_ms = 0.f, prof_rank_ms = 0.f;
   bool rank_pending = false;
   std::vector<cudaEvent_t> ev_pool;  // 3 per chunk of an align call
+  vsg_fallback_fn fallback = nullptr;  // host-side aligner for SHRT_MAX pairs
+  void * fallback_user = nullptr;
   std::vector<vsg_ctx *> children;  // per-host-thread contexts of vsg_search_batch
 };

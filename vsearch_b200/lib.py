@@ -154,6 +154,22 @@ class Context:
             load().vsg_ctx_destroy(self.h)
             self.h = None
 
+    def set_fallback(self, fn):
+        """fn(query_index, strand, target_index) -> 9 ints (score, alnlen, matches, mismatches, gaps,
+        trim_q_left, trim_t_left, trim_q_right, trim_t_right); see vsg_ctx_set_fallback."""
+        proto = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.POINTER(C.c_int64))
+
+        def tramp(_user, q, strand, t, out):
+            try:
+                vals = fn(int(q), int(strand), int(t))
+                for i in range(9):
+                    out[i] = int(vals[i])
+                return 0
+            except Exception:
+                return 1
+        self._fallback_keep = proto(tramp)
+        _check(load().vsg_ctx_set_fallback(self.h, self._fallback_keep, None), "vsg_ctx_set_fallback")
+
     def profile_reset(self):
         _check(load().vsg_profile_reset(self.h), "vsg_profile_reset")
 
