@@ -163,6 +163,21 @@ typedef struct vsg_search_opts {
   int32_t strand_both;    /* --strand both                */
   int32_t mask_lower;     /* queries are soft-masked      */
   int32_t reserved;
+  /* optional accept/reject filters, reference defaults from vsg_search_opts_default():
+     before alignment (search_acceptable_unaligned, core/searchcore.cpp:573-587) */
+  double minqt, maxqt;    /* --minqt / --maxqt : query/target length ratio          */
+  double minsl, maxsl;    /* --minsl / --maxsl : shorter/longer length ratio        */
+  /* after alignment (search_acceptable_aligned, core/searchcore.cpp:671-699) */
+  double maxid;           /* --maxid  (1.0)                */
+  double mid;             /* --mid    (0.0)                */
+  double query_cov;       /* --query_cov (0.0)             */
+  double target_cov;      /* --target_cov (0.0)            */
+  int64_t maxsubs;        /* --maxsubs  (INT_MAX)          */
+  int64_t maxgaps;        /* --maxgaps  (INT_MAX)          */
+  int64_t mincols;        /* --mincols  (0)                */
+  int64_t maxdiffs;       /* --maxdiffs (INT_MAX)          */
+  int32_t leftjust;       /* --leftjust                    */
+  int32_t rightjust;      /* --rightjust                   */
 } vsg_search_opts;
 
 typedef struct vsg_search_result {

@@ -181,6 +181,18 @@ void * vsref_db_create(int n, const char * cat, const int64_t * off, const int *
   return r;
 }
 
+/* optional accept/reject filters of the session (Parameters fields of the same names); order:
+   minqt maxqt minsl maxsl maxid mid query_cov target_cov maxsubs maxgaps mincols maxdiffs leftjust rightjust */
+void vsref_db_set_filters(void * h, const double * v)
+{
+  Parameters & p = static_cast<RefDb *>(h)->params;
+  p.opt_minqt = v[0]; p.opt_maxqt = v[1]; p.opt_minsl = v[2]; p.opt_maxsl = v[3];
+  p.opt_maxid = v[4]; p.opt_mid = v[5]; p.opt_query_cov = v[6]; p.opt_target_cov = v[7];
+  p.opt_maxsubs = static_cast<int64_t>(v[8]); p.opt_maxgaps = static_cast<int64_t>(v[9]);
+  p.opt_mincols = static_cast<int64_t>(v[10]); p.opt_maxdiffs = static_cast<int64_t>(v[11]);
+  p.opt_leftjust = static_cast<int64_t>(v[12]); p.opt_rightjust = static_cast<int64_t>(v[13]);
+}
+
 void vsref_db_free(void * h)
 {
   RefDb * r = static_cast<RefDb *>(h);

@@ -209,3 +209,55 @@ def test_long_queries_rank_vs_oracle(ctx):
         s, c = od.topscores(q, opts)
         assert seqno[i, :nc[i]].tolist() == s.tolist() and count[i, :nc[i]].tolist() == c.tolist(), i
     od.close(); ix.close(); db.close(); qs.close()
+
+
+@pytest.mark.skipif(checkers.ref() is None, reason="oracle/_ref/libvsref.so not present")
+def test_optional_filters_vs_compiled_reference(ctx):
+    """--minqt/--maxqt/--minsl/--maxsl (pre-alignment rejects consume the reject budget) and
+    --maxsubs/--maxgaps/--mincols/--maxdiffs/--leftjust/--rightjust/--query_cov/--target_cov/--maxid/--mid"""
+    import ctypes as C
+    rng = np.random.default_rng(47)
+    roots = synth.random_seqs(rng, 8, 320)
+    seqs = []
+    for r in range(8):
+        for _ in range(10):
+            m = synth.mutate(rng, roots[r], float(rng.uniform(0.0, 0.15)))
+            a = int(rng.integers(0, 60)); b = int(rng.integers(0, 60))
+            seqs.append(m[a: m.shape[0] - b].tobytes())       # ragged ends: terminal gaps, length ratios
+    dbs = synth.SeqSet(seqs)
+    queries = [synth.mutate(rng, roots[i % 8], 0.05)[int(rng.integers(0, 40)):].tobytes() for i in range(32)]
+    qss = synth.SeqSet(queries)
+    db = ctx.seqset(dbs); qs = ctx.seqset(qss)
+    ix = ctx.index(db, 8, 0)
+    big = 2147483647.0
+    cases = [
+        dict(minqt=0.9, maxqt=1.1),
+        dict(minsl=0.92, maxsl=0.99),
+        dict(maxsubs=12, maxgaps=2, mincols=250),
+        dict(maxdiffs=20, leftjust=1),
+        dict(rightjust=1, query_cov=0.9, target_cov=0.9),
+        dict(maxid=0.97, mid=93.0),
+    ]
+    for case in cases:
+        v = dict(minqt=0.0, maxqt=1.7976931348623157e308, minsl=0.0, maxsl=1.7976931348623157e308, maxid=1.0, mid=0.0,
+                 query_cov=0.0, target_cov=0.0, maxsubs=big, maxgaps=big, mincols=0.0, maxdiffs=big, leftjust=0.0, rightjust=0.0)
+        v.update(case)
+        order = ["minqt", "maxqt", "minsl", "maxsl", "maxid", "mid", "query_cov", "target_cov", "maxsubs", "maxgaps",
+                 "mincols", "maxdiffs", "leftjust", "rightjust"]
+        r = checkers.RefDb(dbs, id=0.85, maxaccepts=3, maxrejects=6)
+        arr = (C.c_double * 14)(*[float(v[k]) for k in order])
+        checkers.ref().vsref_db_set_filters(C.c_void_p(r.h), arr)
+        want = r.search(qss, max_results=r.tophits)
+        th = r.tophits
+        r.close()
+        o = gpu_opts(0.85, 3, 6)
+        for k in order:
+            setattr(o, k, type(getattr(o, k))(v[k]))
+        res, counts, _ = ctx.search(ix, db, qs, 0, len(queries), o, th)
+        nrows = 0
+        for i in range(len(queries)):
+            got = rows_of(res, counts, i, th)
+            assert got == [list(t) for t in want[i]], (case, i)
+            nrows += len(got)
+        assert nrows > 0, case
+    ix.close(); db.close(); qs.close()

@@ -81,11 +81,29 @@ void finish_hit(Hit & h, const int32_t * trims, int iddef)
   }
 }
 
-// search_acceptable_aligned with every optional filter at its default (searchcore.cpp:664-737)
-bool acceptable_aligned(Hit & h, double opt_id, double opt_weak_id)
+// search_acceptable_unaligned: the length-ratio filters (searchcore.cpp:573-587); the abundance, label
+// and prefix/suffix filters of that function are not offered through this ABI (defaults pass)
+bool acceptable_unaligned(const vsg_search_opts & o, int qseqlen, int64_t dseqlen)
+{
+  return (qseqlen >= o.minqt * static_cast<double>(dseqlen)) &&
+         (qseqlen <= o.maxqt * static_cast<double>(dseqlen)) &&
+         (qseqlen < dseqlen ? qseqlen >= o.minsl * static_cast<double>(dseqlen)
+                            : static_cast<double>(dseqlen) >= o.minsl * qseqlen) &&
+         (qseqlen < dseqlen ? qseqlen <= o.maxsl * static_cast<double>(dseqlen)
+                            : static_cast<double>(dseqlen) <= o.maxsl * qseqlen);
+}
+
+// search_acceptable_aligned (searchcore.cpp:664-737)
+bool acceptable_aligned(Hit & h, double opt_id, double opt_weak_id, const vsg_search_opts & o, int qseqlen, int dseqlen)
 {
   double const mid = 100.0 * h.matches / (h.matches + h.mismatches);  // 0/0 -> NaN fails the test, as in the reference
-  if (h.id >= 100.0 * opt_weak_id && mid >= 0.0 && h.id <= 100.0 * 1.0) {
+  if (h.id >= 100.0 * opt_weak_id && h.mismatches <= o.maxsubs && h.internal_gaps <= o.maxgaps &&
+      h.internal_alignmentlength >= o.mincols &&
+      (o.leftjust == 0 || h.trim_q_left + h.trim_t_left == 0) &&
+      (o.rightjust == 0 || h.trim_q_right + h.trim_t_right == 0) &&
+      (h.matches + h.mismatches >= o.query_cov * qseqlen) &&
+      (h.matches + h.mismatches >= o.target_cov * static_cast<double>(dseqlen)) &&
+      h.id <= 100.0 * o.maxid && mid >= o.mid && (h.mismatches + h.internal_indels <= o.maxdiffs)) {
     if (h.id >= 100.0 * opt_id) { h.accepted = true; h.weak = false; return true; }
     h.rejected = true; h.weak = true; return false;
   }
@@ -109,6 +127,10 @@ extern "C" void vsg_search_opts_default(vsg_search_opts * o)
   if (o == nullptr) { return; }
   o->id = 0.0; o->weak_id = 10.0; o->maxaccepts = 1; o->maxrejects = 32; o->wordlength = 8;
   o->minwordmatches = -1; o->iddef = 2; o->strand_both = 0; o->mask_lower = 0; o->reserved = 0;
+  o->minqt = 0.0; o->maxqt = 1.7976931348623157e308; o->minsl = 0.0; o->maxsl = 1.7976931348623157e308;
+  o->maxid = 1.0; o->mid = 0.0; o->query_cov = 0.0; o->target_cov = 0.0;
+  o->maxsubs = 2147483647; o->maxgaps = 2147483647; o->mincols = 0; o->maxdiffs = 2147483647;
+  o->leftjust = 0; o->rightjust = 0;
 }
 
 extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * db,
@@ -250,7 +272,13 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
           h.target = static_cast<int>(S.cs[S.next]); h.count = S.cc[S.next];
           h.strand = static_cast<int>(si / static_cast<size_t>(bn));
           S.next++;
-          S.delayed++;  // search_acceptable_unaligned: default filters pass every candidate
+          {
+            int const sstrand = static_cast<int>(si / static_cast<size_t>(bn));
+            int64_t const sql = static_cast<int64_t>(si % static_cast<size_t>(bn));
+            int const sqlen = (sstrand == 0 ? queries->h_len[static_cast<size_t>(q0 + b0 + sql)] : rc_set->h_len[static_cast<size_t>(sql)]);
+            if (acceptable_unaligned(*opts, sqlen, db->h_len[static_cast<size_t>(h.target)])) { S.delayed++; }
+            else { h.rejected = true; }
+          }
           S.hit_count++;
           if (S.delayed == MAXDELAYED) { trigger = true; break; }
         }
@@ -339,7 +367,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
             h.matches = static_cast<int>(nal) - h.nwdiff;
             h.mismatches = h.nwdiff - h.nwindels;
             finish_hit(h, trims4, opts->iddef);
-            if (acceptable_aligned(h, opt_id, opt_weak_id)) { S.accepts++; } else { S.rejects++; }
+            if (acceptable_aligned(h, opt_id, opt_weak_id, *opts, qlen, dlen)) { S.accepts++; } else { S.rejects++; }
             ++i;
           }
         }
@@ -471,16 +499,26 @@ extern "C" int vsg_allpairs(vsg_ctx * c, const vsg_seqset * set, int64_t row0, i
 
   auto run_block = [&](vsg_ctx * wc, int64_t bi) -> int {
     int64_t const r0 = block_first[static_cast<size_t>(bi)], r1 = block_first[static_cast<size_t>(bi) + 1];
-    int64_t np = 0;
-    for (int64_t i = r0; i < r1; i++) { np += n - i - 1; }
-    if (np == 0) { return VSG_OK; }
-    std::vector<uint32_t> pq(static_cast<size_t>(np)), pt(static_cast<size_t>(np));
-    int64_t k = 0, cells = 0;
-    for (int64_t i = r0; i < r1; i++) {
-      int64_t tl = 0;
-      for (int64_t j = i + 1; j < n; j++) { pq[static_cast<size_t>(k)] = static_cast<uint32_t>(i); pt[static_cast<size_t>(k)] = static_cast<uint32_t>(j); k++; tl += set->h_len[static_cast<size_t>(j)]; }
-      cells += static_cast<int64_t>(set->h_len[static_cast<size_t>(i)]) * tl;
+    std::vector<uint32_t> pq, pt;
+    int64_t cells = 0;
+    {
+      int64_t cap_pairs = 0;
+      for (int64_t i = r0; i < r1; i++) { cap_pairs += n - i - 1; }
+      pq.reserve(static_cast<size_t>(cap_pairs)); pt.reserve(static_cast<size_t>(cap_pairs));
     }
+    for (int64_t i = r0; i < r1; i++) {
+      int const ql = set->h_len[static_cast<size_t>(i)];
+      int64_t tl = 0;
+      for (int64_t j = i + 1; j < n; j++) {
+        int const dl = set->h_len[static_cast<size_t>(j)];
+        if (!acceptable_unaligned(*opts, ql, dl)) { continue; }  // allpairs_global.cpp:407-414
+        pq.push_back(static_cast<uint32_t>(i)); pt.push_back(static_cast<uint32_t>(j)); tl += dl;
+      }
+      cells += static_cast<int64_t>(ql) * tl;
+    }
+    int64_t const np = static_cast<int64_t>(pq.size());
+    if (np == 0) { return VSG_OK; }
+    int64_t k = 0;
     std::vector<int16_t> sc(static_cast<size_t>(np));
     std::vector<uint16_t> al(static_cast<size_t>(np)), ma(static_cast<size_t>(np)), mi(static_cast<size_t>(np)), ga(static_cast<size_t>(np));
     std::vector<int32_t> tr(static_cast<size_t>(np) * 4);
@@ -489,10 +527,12 @@ extern "C" int vsg_allpairs(vsg_ctx * c, const vsg_seqset * set, int64_t row0, i
     if (r != VSG_OK) { return r; }
     std::vector<vsg_pair_hit> & o = out[static_cast<size_t>(bi)];
     k = 0;
-    for (int64_t i = r0; i < r1; i++) {
+    while (k < np) {
+      int64_t const i = pq[static_cast<size_t>(k)];
       size_t const first = o.size();
       int const qlen = set->h_len[static_cast<size_t>(i)];
-      for (int64_t j = i + 1; j < n; j++, k++) {
+      for (; k < np && pq[static_cast<size_t>(k)] == i; k++) {
+        int64_t const j = pt[static_cast<size_t>(k)];
         int64_t fb[9];
         bool const diverted = (sc[static_cast<size_t>(k)] == VSG_SCORE_SENTINEL);
         if (diverted && (c->fallback == nullptr || c->fallback(c->fallback_user, i, 0, j, fb) != 0)) {
@@ -519,7 +559,7 @@ extern "C" int vsg_allpairs(vsg_ctx * c, const vsg_seqset * set, int64_t row0, i
         h.matches = static_cast<int>(nal) - h.nwdiff;
         h.mismatches = h.nwdiff - h.nwindels;
         finish_hit(h, trims4, opts->iddef);
-        if (acceptable_aligned(h, opt_id, opt_weak_id)) {
+        if (acceptable_aligned(h, opt_id, opt_weak_id, *opts, qlen, dlen)) {
           vsg_pair_hit ph;
           ph.query = static_cast<int32_t>(i); ph.target = h.target; ph.matches = h.matches; ph.mismatches = h.mismatches;
           ph.gaps = h.nwgaps; ph.alignment_length = h.nwalignmentlength; ph.nwscore = h.nwscore;

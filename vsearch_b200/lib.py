@@ -35,7 +35,11 @@ class SearchOpts(C.Structure):
     _fields_ = [("id", C.c_double), ("weak_id", C.c_double), ("maxaccepts", C.c_int32),
                 ("maxrejects", C.c_int32), ("wordlength", C.c_int32), ("minwordmatches", C.c_int32),
                 ("iddef", C.c_int32), ("strand_both", C.c_int32), ("mask_lower", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32),
+                ("minqt", C.c_double), ("maxqt", C.c_double), ("minsl", C.c_double), ("maxsl", C.c_double),
+                ("maxid", C.c_double), ("mid", C.c_double), ("query_cov", C.c_double), ("target_cov", C.c_double),
+                ("maxsubs", C.c_int64), ("maxgaps", C.c_int64), ("mincols", C.c_int64), ("maxdiffs", C.c_int64),
+                ("leftjust", C.c_int32), ("rightjust", C.c_int32)]
 
 
 class Profile(C.Structure):
