@@ -80,6 +80,13 @@ int vsg_seqset_create(vsg_ctx * ctx, const char * cat, const int64_t * off, cons
                       int64_t n, int host, vsg_seqset ** out);
 void vsg_seqset_destroy(vsg_seqset * s);
 int64_t vsg_seqset_count(const vsg_seqset * s);
+/* DUST soft-masking in place on the device: replaces dust() / dust_all() (core/mask.cpp:79-188;
+ * default --qmask dust / --dbmask dust).  Afterwards lower case marks exactly the regions the
+ * reference would have masked; pass mask_lower = 1 to vsg_index_create / vsg_rank / vsg_search_batch. */
+int vsg_seqset_dust(vsg_ctx * ctx, vsg_seqset * s);
+/* the symbol bytes as stored in HBM (bits 0-3 = 4-bit nucleotide code, bit 4 = lower case), in the
+ * order and at the offsets given to vsg_seqset_create; cap >= total sequence bytes.  For tools/tests. */
+int vsg_seqset_symbols(vsg_ctx * ctx, const vsg_seqset * s, uint8_t * out, int64_t cap);
 
 /* ---- batched alignment: replaces search16_qprep + search16 (core/align_simd.cpp:1406-2060)
  *      for npairs (query,target) pairs at once.  qidx[i] indexes `queries`, tidx[i] indexes

@@ -554,15 +554,7 @@ int rank_enqueue(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * queries, 
   *d_status = *d_n + nq;
   VSG_CUDA_OK(cudaMemsetAsync(*d_status, 0, sizeof(int32_t), c->stream));
   if (nq == 0) { return VSG_OK; }
-  // the kernel runs on the context's high-priority stream, ordered after / before the work of the
-  // main stream by events: its CTAs are picked ahead of queued forward-DP CTAs of other contexts,
-  // so the latency-bound ranker and the issue-bound aligner share SMs instead of taking turns
-  static const bool use_hi = std::getenv("VSG_RANK_PRIORITY") != nullptr && std::getenv("VSG_RANK_PRIORITY")[0] == '1';  // measured: no gain on B200, off by default
-  cudaStream_t const rs = use_hi ? c->stream_hi : c->stream;
-  if (use_hi) {
-    VSG_CUDA_OK(cudaEventRecord(c->ev_hi, c->stream));
-    VSG_CUDA_OK(cudaStreamWaitEvent(rs, c->ev_hi, 0));
-  }
+  cudaStream_t const rs = c->stream;
   VSG_CUDA_OK(cudaFuncSetAttribute(rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(RANK_SMEM)));
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -585,7 +577,6 @@ int rank_enqueue(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * queries, 
       *d_status, d_scratch, stride, bitmap_words);
   count_launch();
   VSG_CUDA_OK(cudaEventRecord(c->ev[5], rs));
-  if (use_hi) { VSG_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev[5], 0)); }
   c->rank_pending = true;
   return VSG_OK;
 }

@@ -10,7 +10,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <numeric>
 #include <map>
 #include <mutex>
 #include <chrono>
@@ -212,12 +211,6 @@ extern "C" int vsg_ctx_create(int device, const vsg_scoring * scoring, vsg_ctx *
   const char * db = std::getenv("VSG_DIR_BUDGET_MB");
   if (db != nullptr && std::atoll(db) > 0) { c->dir_budget = static_cast<size_t>(std::atoll(db)) << 20; }
   VSG_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  {
-    int lo = 0, hi = 0;
-    VSG_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    VSG_CUDA_OK(cudaStreamCreateWithPriority(&c->stream_hi, cudaStreamNonBlocking, hi));
-    VSG_CUDA_OK(cudaEventCreateWithFlags(&c->ev_hi, cudaEventDisableTiming));
-  }
   for (auto & ev : c->ev) { VSG_CUDA_OK(cudaEventCreate(&ev)); }
   // the fast kernel leans on VIMNMX.S16x2 predicate semantics: check them on this device once
   int * d_bad = nullptr;
@@ -247,11 +240,9 @@ extern "C" void vsg_ctx_destroy(vsg_ctx * c)
   for (DevBuf * b : {&c->dir, &c->bnd, &c->he, &c->cigar_scratch, &c->cigar_dense, &c->stats,
                      &c->tasks_fast, &c->tasks_exact, &c->pairs, &c->cigar_len, &c->cigar_offs,
                      &c->cub_tmp, &c->rank_tmp, &c->rank_scratch}) { b->release(); }
-  for (PinBuf * b : {&c->h_tasks, &c->h_stats, &c->h_pairs, &c->h_misc}) { b->release(); }
+  for (PinBuf * b : {&c->h_tasks, &c->h_stats}) { b->release(); }
   for (auto & ev : c->ev) { if (ev != nullptr) { cudaEventDestroy(ev); } }
   for (auto & ev : c->ev_pool) { cudaEventDestroy(ev); }
-  if (c->stream_hi != nullptr) { cudaStreamDestroy(c->stream_hi); }
-  if (c->ev_hi != nullptr) { cudaEventDestroy(c->ev_hi); }
   if (c->stream != nullptr) { cudaStreamDestroy(c->stream); }
   delete c;
 }

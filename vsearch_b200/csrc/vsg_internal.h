@@ -111,15 +111,13 @@ struct vsg_seqset {
 struct vsg_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t stream_hi = nullptr;  // high priority: ranker kernels interleave with forward-DP grids
-  cudaEvent_t ev_hi = nullptr;
   vsg_scoring scoring{};
   vsg::ScoreParams sp{};
   bool fast_disabled = false;  // VSG_DISABLE_FAST=1 (tests force the exact kernel)
   // scratch
   vsg::DevBuf dir, bnd, he, cigar_scratch, cigar_dense, stats, tasks_fast, tasks_exact, pairs,
       cigar_len, cigar_offs, cub_tmp, rank_tmp, rank_scratch;
-  vsg::PinBuf h_tasks, h_stats, h_pairs, h_misc;
+  vsg::PinBuf h_tasks, h_stats;
   size_t dir_budget = (size_t)64 << 30;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // cumulative profile since the last vsg_profile_reset (kernel times from cudaEvents on `stream`)

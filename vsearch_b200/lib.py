@@ -130,6 +130,16 @@ class SeqSetHandle:
             load().vsg_seqset_destroy(self.h)
             self.h = None
 
+    def dust(self):
+        """DUST soft-masking in place on the device (vsg_seqset_dust)"""
+        _check(load().vsg_seqset_dust(self.ctx.h, self.h), "vsg_seqset_dust")
+
+    def symbols(self, total: int) -> np.ndarray:
+        out = np.zeros(total, dtype=np.uint8)
+        _check(load().vsg_seqset_symbols(self.ctx.h, self.h, _ptr(out, C.c_uint8), C.c_int64(total)),
+               "vsg_seqset_symbols")
+        return out
+
 
 class IndexHandle:
     def __init__(self, h):
