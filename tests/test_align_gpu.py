@@ -189,3 +189,15 @@ def test_small_direction_budget_chunks():
     pairs = [(i, j) for i in range(len(seqs)) for j in range(i + 1, len(seqs))]
     check(c2, seqs, seqs, pairs)
     c2.close()
+
+
+def test_long_pairs_stay_on_the_fast_kernel(ctx):
+    """q+d up to ~16 000 under default penalties: values reach beyond +-16 000 but not the 16-bit limits"""
+    rng = np.random.default_rng(18)
+    root = np.frombuffer(rand_seq(rng, 4100), dtype=np.uint8)
+    qseqs = [synth.mutate(rng, root, 0.03).tobytes()[:4000], rand_seq(rng, 2500)]
+    tseqs = [synth.mutate(rng, root, 0.05).tobytes() + rand_seq(rng, 1900), rand_seq(rng, 6000),
+             root.tobytes(), rand_seq(rng, 9000)]
+    pairs = [(0, 0), (0, 1), (0, 2), (1, 3), (1, 0)]
+    res = check(ctx, qseqs, tseqs, pairs, expect_kernel="fast")
+    assert int(res.score.min()) < -4000 and int(res.score.max()) > 6000

@@ -14,7 +14,7 @@
 //      (align_simd.cpp:710-717) fall out of the max instructions' predicates and are stored as
 //      R bytes per lane per step, 128*RW contiguous bytes per warp per step.  Queries longer than
 //      32*R rows run as several strips that hand the boundary row over through HBM.
-//      Arithmetic is exact integer arithmetic in a biased 16-bit representation; the host only
+//      Arithmetic is exact integer arithmetic in a biased (+0x8000) unsigned 16-bit representation; the host only
 //      sends a pair here when a bound on every intermediate proves that neither saturation nor the
 //      reference's overflow flag can occur (vsg_api.cu: fast_path_ok), in which case the
 //      reference's saturating arithmetic is plain integer arithmetic too.
@@ -33,8 +33,11 @@
 
 namespace vsg {
 
-constexpr uint32_t BIAS = 0x4000u;
-constexpr uint32_t BIAS2 = 0x40004000u;
+// every DP value v is held as the unsigned halfword v + 0x8000: the whole non-saturating range of
+// the reference's signed cells, ordered correctly under UNSIGNED compares, and never negative, so
+// 32-bit adds/subtracts of packed pairs cannot carry between the halves
+constexpr uint32_t BIAS = 0x8000u;
+constexpr uint32_t BIAS2 = 0x80008000u;
 constexpr int FAST_WARPS = 4;        // warps per CTA
 constexpr int FAST_RMAX = 16;        // rows per lane
 constexpr int RING = 64;             // column records per warp
@@ -47,12 +50,12 @@ __device__ __forceinline__ uint32_t pk2(int lo, int hi)
 }
 __device__ __forceinline__ uint32_t pk1(int v) { return pk2(v, v); }
 
-// per-halfword signed max; ORs bit_lo / bit_hi into w where b > a strictly (i.e. NOT a >= b)
+// per-halfword unsigned max; ORs bit_lo / bit_hi into w where b > a strictly (i.e. NOT a >= b)
 __device__ __forceinline__ uint32_t max_flag(uint32_t a, uint32_t b, uint32_t & w,
                                              uint32_t bit_lo, uint32_t bit_hi)
 {
   bool ph, pl;
-  uint32_t const m = __vibmax_s16x2(a, b, &ph, &pl);  // VIMNMX.S16x2 with predicate outputs
+  uint32_t const m = __vibmax_u16x2(a, b, &ph, &pl);  // VIMNMX.U16x2 with predicate outputs
   if (!pl) { w |= bit_lo; }
   if (!ph) { w |= bit_hi; }
   return m;
@@ -81,12 +84,12 @@ __global__ void dpx_selftest_kernel(int * bad, int a0, int a1, int b0, int b1, i
 {
   bool ph, pl;
   // halves: lo = (5 vs 7) -> max 7, pred(a>=b)=false ; hi = (9 vs 9) -> pred true
-  uint32_t m = __vibmax_s16x2(pk2(a0, a1), pk2(b0, b1), &ph, &pl);
+  uint32_t m = __vibmax_u16x2(pk2(a0, a1), pk2(b0, b1), &ph, &pl);
   int b = 0;
   if (m != pk2(7, 9) || pl || !ph) { b |= 1; }
-  // negative halves: lo = (-3 vs -4) -> -3, pred true; hi = (-10 vs 2) -> 2, pred false
-  m = __vibmax_s16x2(pk2(c0, c1), pk2(d0, d1), &ph, &pl);
-  if (m != pk2(-3, 2) || !pl || ph) { b |= 2; }
+  // large halves (unsigned order): lo = (0xfffd vs 0xfffc) -> pred true; hi = (0x0002 vs 0xfff6) -> 0xfff6, pred false
+  m = __vibmax_u16x2(pk2(c0, d1), pk2(d0, c1), &ph, &pl);
+  if (m != pk2(-3, -10) || !pl || ph) { b |= 2; }
   if (__vadd2(pk2(c0, 100), pk2(d1, -7)) != pk2(-1, 93)) { b |= 4; }
   *bad = b;
 }

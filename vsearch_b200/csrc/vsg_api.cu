@@ -175,7 +175,7 @@ static inline bool fast_path_ok(const FastBound & fb, int Qpad, int D)
   if (!fb.valid) { return false; }
   int64_t const lb = -(fb.G + static_cast<int64_t>(Qpad) * fb.Rm) - fb.G - static_cast<int64_t>(D + 4) * fb.Rm - 2 * fb.G + fb.smin;
   int64_t const ub = fb.smax * std::min<int64_t>(Qpad, D + 4) + fb.smax;
-  return lb > -16000 && ub < 16000;
+  return lb > -32700 && ub < 32700;  // inside the reference's own no-overflow range (score_min = SHRT_MIN + G, SHRT_MAX)
 }
 
 }  // namespace vsg
