@@ -228,6 +228,11 @@ typedef struct vsg_pair_hit {
   int32_t internal_alignment_length;
   double id;
 } vsg_pair_hit;
+/* Row ranges of equal DP work for `nparts` workers (GPUs): bounds[p] .. bounds[p+1] are the rows of
+ * part p, chosen so that every part has about the same sum over its rows i of len[i] * (sum of len[j],
+ * j > i) — the triangle balancing SURVEY.md §8(e) asks for; equal row counts would give the first
+ * GPU almost twice the work of the average.  Pure host arithmetic; bounds has nparts+1 entries. */
+int vsg_allpairs_partition(const int32_t * len, int64_t n, int nparts, int64_t * bounds);
 int vsg_allpairs(vsg_ctx * ctx, const vsg_seqset * set, int64_t row0, int64_t nrows,
                  const vsg_search_opts * opts, vsg_pair_hit * hits, int64_t cap, int64_t * nhits,
                  int64_t * work);

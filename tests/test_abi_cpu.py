@@ -39,3 +39,23 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(d, f)).read()
                 assert "liboracle" not in text and "oracle/" not in text and "checkers" not in text, f
+
+
+def test_allpairs_partition_balances_the_triangle():
+    """pure host arithmetic behind the multi-GPU row sharding of --allpairs_global (no device needed)"""
+    import numpy as np
+    lib = vlib.load()
+    rng = np.random.default_rng(3)
+    lens = rng.integers(50, 450, size=5000).astype(np.int32)
+    for nparts in (1, 2, 3, 8):
+        b = np.zeros(nparts + 1, dtype=np.int64)
+        rc = lib.vsg_allpairs_partition(lens.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int64(len(lens)), C.c_int(nparts),
+                                        b.ctypes.data_as(C.POINTER(C.c_int64)))
+        assert rc == 0 and b[0] == 0 and b[-1] == len(lens) and np.all(np.diff(b) >= 0)
+        suffix = np.concatenate([np.cumsum(lens[::-1].astype(np.float64))[::-1][1:], [0.0]])
+        work = lens * suffix
+        parts = np.array([work[b[p]:b[p + 1]].sum() for p in range(nparts)])
+        assert parts.max() <= 1.02 * parts.mean() + work.max()
+        if nparts > 1:   # equal row counts would be badly skewed
+            eq = np.array([w.sum() for w in np.array_split(work, nparts)])
+            assert eq.max() / eq.mean() > parts.max() / parts.mean()

@@ -452,6 +452,24 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
 
 
 // ---- all-against-all -----------------------------------------------------------------------------
+extern "C" int vsg_allpairs_partition(const int32_t * len, int64_t n, int nparts, int64_t * bounds)
+{
+  if (n < 0 || nparts < 1 || bounds == nullptr || (n > 0 && len == nullptr)) { Error::set("vsg_allpairs_partition: bad argument"); return VSG_EINVAL; }
+  // cells(i) = len[i] * sum_{j>i} len[j]
+  std::vector<double> row(static_cast<size_t>(n));
+  double suffix = 0.0, total = 0.0;
+  for (int64_t i = n - 1; i >= 0; i--) { row[static_cast<size_t>(i)] = static_cast<double>(len[i]) * suffix; suffix += len[i]; total += row[static_cast<size_t>(i)]; }
+  bounds[0] = 0;
+  double acc = 0.0;
+  int p = 1;
+  for (int64_t i = 0; i < n && p < nparts; i++) {
+    acc += row[static_cast<size_t>(i)];
+    while (p < nparts && acc >= total * p / nparts) { bounds[p++] = i + 1; }
+  }
+  while (p <= nparts) { bounds[p++] = n; }
+  return VSG_OK;
+}
+
 extern "C" int vsg_allpairs(vsg_ctx * c, const vsg_seqset * set, int64_t row0, int64_t nrows,
                             const vsg_search_opts * opts, vsg_pair_hit * hits, int64_t cap, int64_t * nhits,
                             int64_t * work)
