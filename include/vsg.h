@@ -169,7 +169,9 @@ typedef struct vsg_search_opts {
   int32_t iddef;          /* --iddef (default 2)          */
   int32_t strand_both;    /* --strand both                */
   int32_t mask_lower;     /* queries are soft-masked      */
-  int32_t reserved;
+  int32_t lazy;           /* 0 (default): align exactly the groups of <= 8 candidates the reference
+                             hands to search16; 1: align a candidate only when the replay is about to
+                             examine it (same decisions and hit tables, fewer DP cells)           */
   /* optional accept/reject filters, reference defaults from vsg_search_opts_default():
      before alignment (search_acceptable_unaligned, core/searchcore.cpp:573-587) */
   double minqt, maxqt;    /* --minqt / --maxqt : query/target length ratio          */
@@ -202,8 +204,9 @@ typedef struct vsg_search_result {
 } vsg_search_result;
 
 void vsg_search_opts_default(vsg_search_opts * o);
-/* results[(q)*max_results + j], counts[q]; work (optional, 2 x int64): pairs and DP cells handed
- * to the aligner — the reference's search16 workload for the same queries. */
+/* results[(q)*max_results + j], counts[q]; work (optional, 4 x int64): {pairs, DP cells} the
+ * reference's driver hands to search16 for the same queries, then {pairs, DP cells} actually
+ * aligned here (identical unless opts->lazy). */
 int vsg_search_batch(vsg_ctx * ctx, const vsg_index * ix, const vsg_seqset * db,
                      const vsg_seqset * queries, int64_t q0, int64_t nq,
                      const vsg_search_opts * opts, vsg_search_result * results, int max_results,

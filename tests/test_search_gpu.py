@@ -63,6 +63,15 @@ def test_rank_and_search_golden(ctx):
             else:
                 assert got == want, (case["id"], i, got, want)
         assert work[0] > 0 and work[1] > 0
+        # lazy alignment: same hit tables and the same reference-equivalent workload, fewer cells aligned
+        o.lazy = 1
+        res2, counts2, work2 = ctx.search(ix, db, qs, 0, nq, o, th)
+        assert counts2.tolist() == counts.tolist()
+        for i in range(nq):
+            assert rows_of(res2, counts2, i, th) == rows_of(res, counts, i, th), (case["id"], i)
+        assert (int(work2[0]), int(work2[1])) == (int(work[0]), int(work[1]))
+        assert (int(work[2]), int(work[3])) == (int(work[0]), int(work[1]))
+        assert 0 < work2[2] <= work[0] and 0 < work2[3] <= work[1]
     ix.close(); db.close(); qs.close()
 
 
@@ -139,6 +148,11 @@ def test_search_vs_compiled_reference(ctx):
         assert got == [list(t) for t in want[i]], i
         hit += bool(got) and got[0][0] == int(src[i])
     assert hit > 100
+    ol = gpu_opts(0.9, 1, 32); ol.lazy = 1
+    res2, counts2, work2 = ctx.search(ix, db, qs, 0, len(qss), ol, th)
+    for i in range(len(qss)):
+        assert rows_of(res2, counts2, i, th) == [list(t) for t in want[i]], i
+    assert work2[2] * 4 < work2[0]     # the first candidate is almost always accepted: ~1 of 8 pairs aligned
     ix.close(); db.close(); qs.close()
 
 

@@ -57,6 +57,8 @@ struct QState {
   const uint32_t * cc = nullptr;
   int hit_base = 0;  // index of this state's first Hit in the batch-wide hit array
   int hit_count = 0, accepts = 0, rejects = 0, finalized = 0, delayed = 0;
+  int gpos = -1;  // lazy mode: next hit of the open group to examine (-1: no group open)
+  int gend = 0, greq = 0;  // lazy mode: end of the requested hit range, number of pairs requested
   bool done = false, waiting = false;
 };
 
@@ -126,7 +128,7 @@ extern "C" void vsg_search_opts_default(vsg_search_opts * o)
 {
   if (o == nullptr) { return; }
   o->id = 0.0; o->weak_id = 10.0; o->maxaccepts = 1; o->maxrejects = 32; o->wordlength = 8;
-  o->minwordmatches = -1; o->iddef = 2; o->strand_both = 0; o->mask_lower = 0; o->reserved = 0;
+  o->minwordmatches = -1; o->iddef = 2; o->strand_both = 0; o->mask_lower = 0; o->lazy = 0;
   o->minqt = 0.0; o->maxqt = 1.7976931348623157e308; o->minsl = 0.0; o->maxsl = 1.7976931348623157e308;
   o->maxid = 1.0; o->mid = 0.0; o->query_cov = 0.0; o->target_cov = 0.0;
   o->maxsubs = 2147483647; o->maxgaps = 2147483647; o->mincols = 0; o->maxdiffs = 2147483647;
@@ -160,9 +162,10 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   int const minwordmatches = opts->minwordmatches < 0 ? minwordmatches_defaults[opts->wordlength] : opts->minwordmatches;
   double const opt_id = opts->id;
   double const opt_weak_id = (opts->id >= 0.0 && opts->weak_id > opts->id) ? opts->id : opts->weak_id;
-  int64_t total_pairs = 0, total_cells = 0;
+  int64_t total_pairs = 0, total_cells = 0, aligned_pairs = 0, aligned_cells = 0;
+  bool const lazy = opts->lazy != 0;
   for (int64_t q = 0; q < nq; q++) { counts[q] = 0; }
-  if (seqcount == 0 || nq == 0) { if (work) { work[0] = 0; work[1] = 0; } return VSG_OK; }
+  if (seqcount == 0 || nq == 0) { if (work) { work[0] = work[1] = work[2] = work[3] = 0; } return VSG_OK; }
   if (tophits64 > 1024) { Error::set("vsg_search_batch: maxaccepts+maxrejects+8 > 1024 is not supported on the device ranker"); return VSG_EINVAL; }
   int const tophits = static_cast<int>(tophits64);
   int const nstrands = opts->strand_both ? 2 : 1;
@@ -188,7 +191,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   }
 
   vsg_ctx * const parent = c;
-  auto run_batch = [&](vsg_ctx * c, int64_t b0, int64_t & total_pairs, int64_t & total_cells) -> int {
+  auto run_batch = [&](vsg_ctx * c, int64_t b0, int64_t & total_pairs, int64_t & total_cells, int64_t & al_pairs, int64_t & al_cells) -> int {
   std::vector<uint32_t> h_seqno, h_count;
   std::vector<int32_t> h_n;
   std::vector<QState> st;
@@ -261,6 +264,66 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
       any = false;
       pq.clear(); pt.clear(); pstate.clear();
       // gather: run each active query's candidate loop up to its next align_delayed (searchcore.cpp:915-954)
+      if (lazy) {
+        // same decisions, alignments on demand: open the group the reference would hand to search16,
+        // but align only the hit the replay is about to examine
+        for (size_t si = 0; si < st.size(); si++) {
+          QState & S = st[si];
+          if (S.done) { continue; }
+          int const strand = static_cast<int>(si / static_cast<size_t>(bn));
+          int64_t const ql = static_cast<int64_t>(si % static_cast<size_t>(bn));
+          int const sqlen = (strand == 0 ? queries->h_len[static_cast<size_t>(q0 + b0 + ql)] : rc_set->h_len[static_cast<size_t>(ql)]);
+          for (;;) {
+            if (S.gpos < 0) {
+              bool trigger = false;
+              while ((S.finalized + S.delayed < maxaccepts + maxrejects - 1) && (S.rejects < maxrejects) &&
+                     (S.accepts < maxaccepts) && (S.next < S.ncand)) {
+                Hit & h = hits[static_cast<size_t>(S.hit_base) + S.hit_count];
+                std::memset(&h, 0, sizeof(Hit));
+                h.target = static_cast<int>(S.cs[S.next]); h.count = S.cc[S.next]; h.strand = strand;
+                S.next++;
+                if (acceptable_unaligned(*opts, sqlen, db->h_len[static_cast<size_t>(h.target)])) { S.delayed++; }
+                else { h.rejected = true; }
+                S.hit_count++;
+                if (S.delayed == MAXDELAYED) { trigger = true; break; }
+              }
+              if (!trigger && S.delayed == 0) { S.done = true; break; }
+              S.gpos = S.finalized;
+              for (int x = S.finalized; x < S.hit_count; x++) {   // what the reference's search16 call covers
+                Hit const & h = hits[static_cast<size_t>(S.hit_base) + x];
+                if (!h.rejected) { total_pairs++; total_cells += static_cast<int64_t>(sqlen) * db->h_len[static_cast<size_t>(h.target)]; }
+              }
+            }
+            bool need = false;
+            while (S.gpos < S.hit_count && S.rejects < maxrejects && S.accepts < maxaccepts) {
+              Hit const & h = hits[static_cast<size_t>(S.hit_base) + S.gpos];
+              if (h.rejected) { S.rejects++; S.gpos++; continue; }
+              need = true;
+              break;
+            }
+            if (need) {
+              // the group's first candidate alone (it is accepted most of the time); if the replay gets
+              // past it, the rest of the group in one go — at most two device round trips per group
+              int const xend = (S.gpos == S.finalized) ? S.gpos + 1 : S.hit_count;
+              S.greq = 0;
+              for (int x = S.gpos; x < xend; x++) {
+                Hit const & h = hits[static_cast<size_t>(S.hit_base) + x];
+                if (h.rejected) { continue; }
+                pq.push_back(static_cast<uint32_t>(strand == 0 ? q0 + b0 + ql : ql));
+                pt.push_back(static_cast<uint32_t>(h.target));
+                pstate.push_back(static_cast<int>(si));
+                S.greq++;
+              }
+              S.gend = xend;
+              S.waiting = true;
+              any = true;
+              break;
+            }
+            // group exhausted or a limit reached: align_delayed ends, the candidate loop resumes
+            S.finalized = S.hit_count; S.delayed = 0; S.gpos = -1;
+          }
+        }
+      } else
       for (size_t si = 0; si < st.size(); si++) {
         QState & S = st[si];
         if (S.done) { continue; }
@@ -317,7 +380,8 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
                                       a_ga.data() + lo, a_tr.data() + 4 * lo, nullptr, 0, nullptr);
         if (r != VSG_OK) { if (rc_set) { vsg_seqset_destroy(rc_set); } return r; }
       }
-      total_pairs += static_cast<int64_t>(np);
+      if (!lazy) { total_pairs += static_cast<int64_t>(np); }
+      al_pairs += static_cast<int64_t>(np);
       t_align += ms(tp0, now()); tp0 = now();
       // replay: the second half of align_delayed (searchcore.cpp:780-880)
       size_t pi = 0;
@@ -329,11 +393,16 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
         int const strand = static_cast<int>(si / static_cast<size_t>(bn));
         int const qlen = (strand == 0 ? queries->h_len[static_cast<size_t>(q0 + b0 + ql)] : rc_set->h_len[static_cast<size_t>(ql)]);
         size_t i = pi;
-        for (int x = S.finalized; x < S.hit_count; x++) {
+        int const xlo = lazy ? S.gpos : S.finalized, xhi = lazy ? S.gend : S.hit_count;
+        for (int x = xlo; x < xhi; x++) {
           Hit & h = hits[static_cast<size_t>(S.hit_base) + x];
-          if (!h.rejected) { total_cells += static_cast<int64_t>(qlen) * db->h_len[static_cast<size_t>(h.target)]; }
+          if (!h.rejected) {
+            int64_t const cl = static_cast<int64_t>(qlen) * db->h_len[static_cast<size_t>(h.target)];
+            al_cells += cl;
+            if (!lazy) { total_cells += cl; }
+          }
         }
-        for (int x = S.finalized; x < S.hit_count; x++) {
+        for (int x = xlo; x < xhi; x++) {
           if (S.rejects < maxrejects && S.accepts < maxaccepts) {
             Hit & h = hits[static_cast<size_t>(S.hit_base) + x];
             if (h.rejected) { S.rejects++; continue; }
@@ -375,8 +444,8 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
         size_t mine = 0;
         while (pi + mine < np && static_cast<size_t>(pstate[pi + mine]) == si) { mine++; }
         pi += mine;
-        S.finalized = S.hit_count;
-        S.delayed = 0;
+        if (lazy) { S.gpos = S.gend; }
+        else { S.finalized = S.hit_count; S.delayed = 0; }
       }
       t_replay += ms(tp0, now());
     }
@@ -418,13 +487,13 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   std::atomic<int64_t> next{0};
   std::vector<int> rcs(static_cast<size_t>(nthreads), VSG_OK);
   std::vector<std::string> msgs(static_cast<size_t>(nthreads));
-  std::vector<int64_t> tp(static_cast<size_t>(nthreads), 0), tc(static_cast<size_t>(nthreads), 0);
+  std::vector<int64_t> tp(static_cast<size_t>(nthreads), 0), tc(static_cast<size_t>(nthreads), 0), ap(static_cast<size_t>(nthreads), 0), ac(static_cast<size_t>(nthreads), 0);
   auto worker = [&](int t) {
     vsg_ctx * wc = c->children[static_cast<size_t>(t)];
     for (;;) {
       int64_t const bi = next.fetch_add(1);
       if (bi >= nbatches) { break; }
-      int const r = run_batch(wc, bi * BATCH, tp[static_cast<size_t>(t)], tc[static_cast<size_t>(t)]);
+      int const r = run_batch(wc, bi * BATCH, tp[static_cast<size_t>(t)], tc[static_cast<size_t>(t)], ap[static_cast<size_t>(t)], ac[static_cast<size_t>(t)]);
       if (r != VSG_OK) { rcs[static_cast<size_t>(t)] = r; msgs[static_cast<size_t>(t)] = vsg_last_error(); next.store(nbatches); break; }
     }
   };
@@ -442,11 +511,12 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
     c->prof_fwd_ms += wc->prof_fwd_ms; c->prof_tb_ms += wc->prof_tb_ms; c->prof_rank_ms += wc->prof_rank_ms;
     vsg_profile_reset(wc);
     total_pairs += tp[static_cast<size_t>(t)]; total_cells += tc[static_cast<size_t>(t)];
+    aligned_pairs += ap[static_cast<size_t>(t)]; aligned_cells += ac[static_cast<size_t>(t)];
   }
   for (int t = 0; t < nthreads; t++) {
     if (rcs[static_cast<size_t>(t)] != VSG_OK) { Error::set(msgs[static_cast<size_t>(t)]); return rcs[static_cast<size_t>(t)]; }
   }
-  if (work != nullptr) { work[0] = total_pairs; work[1] = total_cells; }
+  if (work != nullptr) { work[0] = total_pairs; work[1] = total_cells; work[2] = aligned_pairs; work[3] = aligned_cells; }
   return VSG_OK;
 }
 

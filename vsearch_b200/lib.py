@@ -35,7 +35,7 @@ class SearchOpts(C.Structure):
     _fields_ = [("id", C.c_double), ("weak_id", C.c_double), ("maxaccepts", C.c_int32),
                 ("maxrejects", C.c_int32), ("wordlength", C.c_int32), ("minwordmatches", C.c_int32),
                 ("iddef", C.c_int32), ("strand_both", C.c_int32), ("mask_lower", C.c_int32),
-                ("reserved", C.c_int32),
+                ("lazy", C.c_int32),
                 ("minqt", C.c_double), ("maxqt", C.c_double), ("minsl", C.c_double), ("maxsl", C.c_double),
                 ("maxid", C.c_double), ("mid", C.c_double), ("query_cov", C.c_double), ("target_cov", C.c_double),
                 ("maxsubs", C.c_int64), ("maxgaps", C.c_int64), ("mincols", C.c_int64), ("maxdiffs", C.c_int64),
@@ -273,7 +273,7 @@ class Context:
                opts: SearchOpts, max_results: int):
         res = (SearchResult * (nq * max_results))()
         counts = np.zeros(nq, dtype=np.int32)
-        work = np.zeros(2, dtype=np.int64)
+        work = np.zeros(4, dtype=np.int64)
         _check(load().vsg_search_batch(self.h, ix.h, db.h, qs.h, C.c_int64(q0), C.c_int64(nq),
                                        C.byref(opts), res, C.c_int(max_results), _ptr(counts, C.c_int32),
                                        _ptr(work, C.c_int64)), "vsg_search_batch")
