@@ -1,6 +1,7 @@
 """GPU parity of the k-mer ranker (vsg_rank) and the whole search path (vsg_search_batch) against
 the golden fixtures, the oracle and — when oracle/_ref travelled along — the unmodified reference."""
 import json
+import contextlib
 import os
 
 import numpy as np
@@ -40,6 +41,16 @@ def gpu_opts(id, maxaccepts, maxrejects, strand_both=0, mask_lower=0, k=8):
     return o
 
 
+@contextlib.contextmanager
+def no_tail():
+    """VSG_TAIL_PAIRS=0: never prefetch the remaining candidates of the last few active queries"""
+    os.environ["VSG_TAIL_PAIRS"] = "0"
+    try:
+        yield
+    finally:
+        del os.environ["VSG_TAIL_PAIRS"]
+
+
 def test_rank_and_search_golden(ctx):
     g = load("rank_search_vectors.json")
     dbs = synth.SeqSet([d.encode() for d in g["db"]])
@@ -63,15 +74,30 @@ def test_rank_and_search_golden(ctx):
             else:
                 assert got == want, (case["id"], i, got, want)
         assert work[0] > 0 and work[1] > 0
+        # the default run above took the "tail" shortcut at once (few queries: all remaining candidates
+        # in one device call); without it the driver aligns exactly the reference's pairs
+        with no_tail():
+            res1, counts1, work1 = ctx.search(ix, db, qs, 0, nq, o, th)
+        assert counts1.tolist() == counts.tolist()
+        for i in range(nq):
+            assert rows_of(res1, counts1, i, th) == rows_of(res, counts, i, th), (case["id"], i)
+        assert (int(work1[0]), int(work1[1])) == (int(work[0]), int(work[1]))
+        assert (int(work1[2]), int(work1[3])) == (int(work[0]), int(work[1]))
+        assert work[2] >= work[0] and work[3] >= work[1]
         # lazy alignment: same hit tables and the same reference-equivalent workload, fewer cells aligned
         o.lazy = 1
-        res2, counts2, work2 = ctx.search(ix, db, qs, 0, nq, o, th)
-        assert counts2.tolist() == counts.tolist()
-        for i in range(nq):
-            assert rows_of(res2, counts2, i, th) == rows_of(res, counts, i, th), (case["id"], i)
-        assert (int(work2[0]), int(work2[1])) == (int(work[0]), int(work[1]))
-        assert (int(work[2]), int(work[3])) == (int(work[0]), int(work[1]))
-        assert 0 < work2[2] <= work[0] and 0 < work2[3] <= work[1]
+        for tail in (True, False):
+            if tail:
+                res2, counts2, work2 = ctx.search(ix, db, qs, 0, nq, o, th)
+            else:
+                with no_tail():
+                    res2, counts2, work2 = ctx.search(ix, db, qs, 0, nq, o, th)
+            assert counts2.tolist() == counts.tolist()
+            for i in range(nq):
+                assert rows_of(res2, counts2, i, th) == rows_of(res, counts, i, th), (case["id"], i, tail)
+            assert (int(work2[0]), int(work2[1])) == (int(work[0]), int(work[1]))
+            if not tail:
+                assert 0 < work2[2] <= work[0] and 0 < work2[3] <= work[1]
     ix.close(); db.close(); qs.close()
 
 
@@ -149,10 +175,22 @@ def test_search_vs_compiled_reference(ctx):
         hit += bool(got) and got[0][0] == int(src[i])
     assert hit > 100
     ol = gpu_opts(0.9, 1, 32); ol.lazy = 1
-    res2, counts2, work2 = ctx.search(ix, db, qs, 0, len(qss), ol, th)
+    with no_tail():
+        res2, counts2, work2 = ctx.search(ix, db, qs, 0, len(qss), ol, th)
     for i in range(len(qss)):
         assert rows_of(res2, counts2, i, th) == [list(t) for t in want[i]], i
     assert work2[2] * 4 < work2[0]     # the first candidate is almost always accepted: ~1 of 8 pairs aligned
+    # the tail shortcut entered after ordinary rounds (threshold below the first round's size), and at once
+    for tail_pairs in ("16", "100000"):
+        os.environ["VSG_TAIL_PAIRS"] = tail_pairs
+        try:
+            for o in (gpu_opts(0.9, 1, 32), ol):
+                res3, counts3, work3 = ctx.search(ix, db, qs, 0, len(qss), o, th)
+                for i in range(len(qss)):
+                    assert rows_of(res3, counts3, i, th) == [list(t) for t in want[i]], (tail_pairs, o.lazy, i)
+                assert (int(work3[0]), int(work3[1])) == (int(work2[0]), int(work2[1]))
+        finally:
+            del os.environ["VSG_TAIL_PAIRS"]
     ix.close(); db.close(); qs.close()
 
 

@@ -23,6 +23,8 @@ for rep in range(3):
     res = ctx.align_pairs(qs, db, qi, ti)
     w = time.time() - t0
     print(f"align {qi.shape[0]} pairs: fwd {res.fwd_ms:.1f} ms tb {res.tb_ms:.1f} ms wall {1e3*w:.1f} ms -> fwd {res.cells/res.fwd_ms/1e6:.0f} GCUPS")
+if "--short" in sys.argv:
+    sys.exit(0)
 opts = vlib.default_search_opts(); opts.id = 0.9
 for thr in (1, 2, 4, 8):
     os.environ["VSG_HOST_THREADS"] = str(thr)

@@ -9,7 +9,7 @@ ctx = vlib.Context(0)
 db = ctx.seqset(synth.SeqSet.from_matrix(dbm)); ix = ctx.index(db, 8, 0)
 qs_h, _ = synth.config2_query_batch(dbm, NQ, batch=1); qs = ctx.seqset(qs_h)
 opts = vlib.default_search_opts(); opts.id = 0.9
-for thr in (1, 4):
+for thr in (8,):
     os.environ["VSG_HOST_THREADS"] = str(thr)
     for rep in range(2):
         print(f"--- threads {thr} rep {rep}", file=sys.stderr, flush=True)

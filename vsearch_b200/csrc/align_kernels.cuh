@@ -31,6 +31,8 @@
 
 #include "vsg_internal.h"
 
+#include <type_traits>
+
 namespace vsg {
 
 // every DP value v is held as the unsigned halfword v + 0x8000: the whole non-saturating range of
@@ -94,33 +96,50 @@ __global__ void dpx_selftest_kernel(int * bad, int a0, int a1, int b0, int b1, i
   *bad = b;
 }
 
-template <int R, bool GENERAL>
+// shared memory the fast kernel needs beyond its static arrays (the per-lane score profile)
+__host__ __device__ constexpr bool fast_has_profile(int R, bool general) { return !general && R <= 8; }
+__host__ __device__ constexpr size_t fast_dyn_smem(int R, bool general)
+{
+  return fast_has_profile(R, general) ? static_cast<size_t>(FAST_WARPS) * 16 * ((R + 3) / 4) * 32 * 16 : 0;
+}
+
+template <int R, bool GENERAL, bool MULTI>
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 nw_fast_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
                const FastTask * __restrict__ tasks, int ntasks,
                uint8_t * __restrict__ dir, uint2 * __restrict__ bnd, int32_t * __restrict__ stats)
 {
   constexpr int RW = (R <= 4 ? 1 : (R <= 8 ? 2 : 4));
-  constexpr int LUT_WORDS = GENERAL ? 4096 : 64 * 32;
+  // PROF: plain-ACGT classes with <= 8 rows per lane read their substitution scores from a per-lane
+  // PROFILE (target-pair code x the lane's own rows) so that one 128-bit load serves four rows
+  constexpr bool PROF = fast_has_profile(R, GENERAL);
+  constexpr int RQ = (R + 3) / 4;
+  constexpr int LUT_WORDS = GENERAL ? 4096 : (PROF ? 32 : 64 * 32);
+  // MULTI: the query needs several strips (only queries longer than 32*FAST_RMAX rows do)
+  extern __shared__ uint4 prof_mem[];
   __shared__ uint32_t lut[LUT_WORDS];
-  __shared__ uint4 ringA[FAST_WARPS][RING];
-  __shared__ uint32_t ringB[FAST_WARPS][RING];
+  // every column record is stored twice, RING entries apart, so that the 32 consecutive records a
+  // lane reads during a chunk are contiguous (no wrap-around arithmetic per step)
+  __shared__ uint4 ringA[FAST_WARPS][2 * RING];
+  __shared__ uint32_t ringB[FAST_WARPS][2 * RING];
 
   int const lane = threadIdx.x & 31;
   int const wib = threadIdx.x >> 5;
 
-  // substitution table: both halves looked up at once
-  for (int e = threadIdx.x; e < LUT_WORDS; e += blockDim.x) {
-    if (GENERAL) {
-      int const q = e >> 8, dlo = e & 15, dhi = (e >> 4) & 15;
-      lut[e] = pk2(sp.S[dlo][q], sp.S[dhi][q]);
-    } else {
-      int const ent = e >> 5;  // replicated for the 32 lanes: word = ent*32 + lane
-      int const q = 1 << (ent >> 4), dlo = 1 << (ent & 3), dhi = 1 << ((ent >> 2) & 3);
-      lut[e] = pk2(sp.S[dlo][q], sp.S[dhi][q]);
+  if (!PROF) {
+    // substitution table: both halves looked up at once
+    for (int e = threadIdx.x; e < LUT_WORDS; e += blockDim.x) {
+      if (GENERAL) {
+        int const q = e >> 8, dlo = e & 15, dhi = (e >> 4) & 15;
+        lut[e] = pk2(sp.S[dlo][q], sp.S[dhi][q]);
+      } else {
+        int const ent = e >> 5;  // replicated for the 32 lanes: word = ent*32 + lane
+        int const q = 1 << (ent >> 4), dlo = 1 << (ent & 3), dhi = 1 << ((ent >> 2) & 3);
+        lut[e] = pk2(sp.S[dlo][q], sp.S[dhi][q]);
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
 
   int const w = blockIdx.x * FAST_WARPS + wib;
   if (w >= ntasks) { return; }
@@ -134,7 +153,7 @@ nw_fast_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
   int const dmax = tk.dmax;
   int const nsteps = dmax + 31;
   int const strip_rows = 32 * R;
-  int const nstrips = (Q + strip_rows - 1) / strip_rows;
+  int const nstrips = MULTI ? (Q + strip_rows - 1) / strip_rows : 1;
   size_t const strip_bytes = static_cast<size_t>(nsteps) * 32 * RW * 4;
 
   int const QRqi = sp.go[Q_I] + sp.ge[Q_I], Rqi = sp.ge[Q_I];
@@ -156,22 +175,17 @@ nw_fast_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
   uint32_t const lut_s = static_cast<uint32_t>(__cvta_generic_to_shared(lut));
   uint32_t const rA_s = static_cast<uint32_t>(__cvta_generic_to_shared(rA));
   uint32_t const rB_s = static_cast<uint32_t>(__cvta_generic_to_shared(rB));
-  {
-    uint32_t a = rA_s, b = rB_s;  // pin the ring addresses in registers (see rowoff below)
-    asm volatile("" : "+r"(a), "+r"(b));
-    const_cast<uint32_t &>(rA_s) = a; const_cast<uint32_t &>(rB_s) = b;
-  }
+  // this lane's column of the profile: entry (tp, r4) sits at prof_s + (tp*RQ + r4)*512
+  uint4 * const myprof = prof_mem + static_cast<size_t>(wib) * 16 * RQ * 32 + lane;
+  uint32_t const prof_s = static_cast<uint32_t>(__cvta_generic_to_shared(myprof));
 
   for (int strip = 0; strip < nstrips; strip++) {
     int const row0 = strip * strip_rows + lane * R;
 
-    uint32_t Hl[R], E[R], rowoff[R], QRq[R], Rq[R];
+    uint32_t Hl[R], E[R], rowoff[PROF ? 1 : R], QRq[R], Rq[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
       int const i = row0 + r;
-      int const code = (i < Q) ? (qsym[i] & 15) : 0;
-      rowoff[r] = lut_s + (GENERAL ? static_cast<uint32_t>(code) * 1024u
-                                   : (static_cast<uint32_t>(code_to_2bit(code)) * 16u * 32u + lane) * 4u);
       bool const last = (i == Q - 1);
       QRq[r] = pk1(last ? QRqr : QRqi);
       Rq[r] = pk1(last ? Rqr : Rqi);
@@ -179,14 +193,122 @@ nw_fast_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
       E[r] = Hl[r] - QRq[r];                       // E(i,0)      (align_simd.cpp:855-857)
       // per-row constants must live in registers: without this ptxas re-derives the "is this the
       // query's last row" select (compare + select + repack) for every row of every step
-      asm volatile("" : "+r"(rowoff[r]), "+r"(QRq[r]), "+r"(Rq[r]));
+      asm volatile("" : "+r"(QRq[r]), "+r"(Rq[r]));
+    }
+    if (PROF) {
+      // rows beyond the query's end score like 'A' (their cells are never read)
+      int code[RQ * 4];
+#pragma unroll
+      for (int r = 0; r < RQ * 4; r++) {
+        int const i = row0 + r;
+        code[r] = (r < R && i < Q) ? (1 << code_to_2bit(qsym[i] & 15)) : 1;
+      }
+      for (int tp = 0; tp < 16; tp++) {
+        int const dlo = 1 << (tp & 3), dhi = 1 << (tp >> 2);
+#pragma unroll
+        for (int r4 = 0; r4 < RQ; r4++) {
+          uint4 v;
+          v.x = pk2(sp.S[dlo][code[4 * r4 + 0]], sp.S[dhi][code[4 * r4 + 0]]);
+          v.y = pk2(sp.S[dlo][code[4 * r4 + 1]], sp.S[dhi][code[4 * r4 + 1]]);
+          v.z = pk2(sp.S[dlo][code[4 * r4 + 2]], sp.S[dhi][code[4 * r4 + 2]]);
+          v.w = pk2(sp.S[dlo][code[4 * r4 + 3]], sp.S[dhi][code[4 * r4 + 3]]);
+          myprof[(tp * RQ + r4) * 32] = v;   // read back by this lane only: no barrier needed
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        int const i = row0 + r;
+        int const code = (i < Q) ? (qsym[i] & 15) : 0;
+        rowoff[r] = lut_s + (GENERAL ? static_cast<uint32_t>(code) * 1024u
+                                     : (static_cast<uint32_t>(code_to_2bit(code)) * 16u * 32u + lane) * 4u);
+        asm volatile("" : "+r"(rowoff[r]));
+      }
     }
     // H(row0-1,-1): the diagonal input of this lane's first row at column 0
     uint32_t diag_in = (row0 == 0) ? BIAS2 : BIAS2 - pk1(gotl + row0 * getl);
     uint32_t Hout = BIAS2, Fout = BIAS2;
     uint8_t * const dstrip = dir + tk.dir_off + static_cast<size_t>(strip) * strip_bytes;
-    bool const write_bnd = (strip + 1 < nstrips) && (lane == 31);
+    bool const write_bnd = MULTI && (strip + 1 < nstrips) && (lane == 31);
     bool const capture = (strip == klast) && (lane == llast);
+    // the steps at which the lane that owns the last row passes the targets' last columns
+    int const cap_lo = (strip == klast) ? Dlo - 1 + llast : -1;
+    int const cap_hi = (strip == klast) ? Dhi - 1 + llast : -1;
+
+    // one step of the wavefront: this lane's R rows of column c.  EDGE steps may find the lane
+    // outside the matrix (ramp-up / ramp-down) and may have to pick up the final score; steady
+    // steps (all 32 lanes inside, no score to capture) skip those tests.
+    auto step = [&](auto edge_tag, int c, uint32_t aA, uint32_t aB, uint32_t * dptr) {
+      constexpr bool EDGE = decltype(edge_tag)::value;
+      uint32_t hin = __shfl_up_sync(0xffffffffu, Hout, 1);
+      uint32_t fin = __shfl_up_sync(0xffffffffu, Fout, 1);
+      if (!EDGE || (c >= 0 && c < dmax)) {
+        uint4 const rec = lds128(aA);
+        if (lane == 0) { hin = rec.w; fin = lds32(aB); }
+
+        // H(i-1,j-1) + S for every row first: the old column is dead before the new one is
+        // produced (no register rotation at the loop edge) and these adds are off the F chain
+        uint32_t t[R];
+        if (PROF) {
+          uint32_t const pa = prof_s + rec.x;
+#pragma unroll
+          for (int r4 = 0; r4 < RQ; r4++) {
+            uint4 const S4 = lds128(pa + r4 * 512u);
+            uint32_t const Sv[4] = {S4.x, S4.y, S4.z, S4.w};
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              int const r = 4 * r4 + u;
+              if (r < R) { t[r] = __vadd2(r == 0 ? diag_in : Hl[r - 1], Sv[u]); }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            uint32_t const S = lds32(rowoff[r] + rec.x);
+            t[r] = __vadd2(r == 0 ? diag_in : Hl[r - 1], S);
+          }
+        }
+        uint32_t F = fin;
+        uint32_t wd[RW];
+#pragma unroll
+        for (int kk = 0; kk < RW; kk++) { wd[kk] = 0; }
+
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          // the 8 flags of this row-step go to a register of their own (a short dependency chain
+          // per row instead of one 32-deep chain per word, which made ptxas park predicates in
+          // P2R/ISETP pairs); one multiply-add per row merges it into the output word
+          uint32_t fb = 0;
+          uint32_t const m1 = max_flag(t[r], F, fb, 1u, 16u);     // up:   F > h
+          uint32_t const h = max_flag(m1, E[r], fb, 2u, 32u);     // left: E > h
+          Hl[r] = h;
+          uint32_t const hf = h - rec.y;                          // H - QR_t
+          uint32_t const f = F - rec.z;                           // F - R_t
+          F = max_flag(hf, f, fb, 4u, 64u);                       // extup:   f > hf
+          uint32_t const he = h - QRq[r];
+          uint32_t const e = E[r] - Rq[r];
+          E[r] = max_flag(he, e, fb, 8u, 128u);                   // extleft: e > he
+          wd[r >> 2] = fb * (1u << (8u * (r & 3))) + wd[r >> 2];
+        }
+        Hout = Hl[R - 1];
+        Fout = F;
+        diag_in = hin;
+
+        if (RW == 1) { dptr[0] = wd[0]; }
+        else if (RW == 2) { *reinterpret_cast<uint2 *>(dptr) = make_uint2(wd[0], wd[1]); }
+        else { *reinterpret_cast<uint4 *>(dptr) = make_uint4(wd[0], wd[1], wd[RW > 2 ? 2 : 0], wd[RW > 3 ? 3 : 0]); }
+
+        if (MULTI && write_bnd) { __stcg(mybnd + c, make_uint2(Hout, Fout)); }
+
+        if (EDGE && capture && (c == Dlo - 1 || c == Dhi - 1)) {
+          uint32_t v = 0;
+#pragma unroll
+          for (int r = 0; r < R; r++) { if (r == rlast) { v = Hl[r]; } }
+          if (c == Dlo - 1) { score_lo = static_cast<int>(v & 0xffffu) - static_cast<int>(BIAS); }
+          if (c == Dhi - 1) { score_hi = static_cast<int>(v >> 16) - static_cast<int>(BIAS); }
+        }
+      }
+    };
 
     uint32_t * dptr = reinterpret_cast<uint32_t *>(dstrip) + static_cast<size_t>(lane) * RW;
     for (int s0 = 0; s0 < nsteps; s0 += 32) {
@@ -199,13 +321,13 @@ nw_fast_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
           int const b = (cc < Dhi) ? (dhi_p[cc] & 15) : 0;
           uint4 rec;
           rec.x = GENERAL ? static_cast<uint32_t>(a + 16 * b) * 4u
-                          : static_cast<uint32_t>(code_to_2bit(a) + 4 * code_to_2bit(b)) * 128u;
+                          : static_cast<uint32_t>(code_to_2bit(a) + 4 * code_to_2bit(b)) * (PROF ? RQ * 512u : 128u);
           // target-gap penalties: right-end values from the target's last column on
           // (align_simd.cpp:1741-1751)
           rec.y = pk2(cc >= Dlo - 1 ? QRtr : QRti, cc >= Dhi - 1 ? QRtr : QRti);
           rec.z = pk2(cc >= Dlo - 1 ? Rtr : Rti, cc >= Dhi - 1 ? Rtr : Rti);
           uint32_t fin0;
-          if (strip == 0) {
+          if (!MULTI || strip == 0) {
             rec.w = BIAS2 - pk1(goql + (cc + 1) * geql);  // H(-1,c)  (align_simd.cpp:1895-1901)
             fin0 = rec.w - rec.y;                         // F(0,c)   (align_simd.cpp:830-833)
           } else {
@@ -213,68 +335,28 @@ nw_fast_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
             rec.w = v.x;
             fin0 = v.y;
           }
-          rA[cc & (RING - 1)] = rec;
-          rB[cc & (RING - 1)] = fin0;
+          int const slot = cc & (RING - 1);
+          rA[slot] = rec; rA[slot + RING] = rec;
+          rB[slot] = fin0; rB[slot + RING] = fin0;
         }
         __syncwarp();
       }
-      int const kend = min(32, nsteps - s0);
-      int c = s0 - lane;
-      for (int k = 0; k < kend; k++, c++, dptr += 32 * RW) {
-        uint32_t hin = __shfl_up_sync(0xffffffffu, Hout, 1);
-        uint32_t fin = __shfl_up_sync(0xffffffffu, Fout, 1);
-        if (c >= 0 && c < dmax) {
-          uint32_t const slot = static_cast<uint32_t>(c) & (RING - 1);
-          uint4 const rec = lds128(rA_s + slot * 16u);
-          if (lane == 0) { hin = rec.w; fin = lds32(rB_s + slot * 4u); }
-
-          // H(i-1,j-1) + S for every row first: the old column is dead before the new one is
-          // produced (no register rotation at the loop edge) and these adds are off the F chain
-          uint32_t t[R];
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            uint32_t const S = lds32(rowoff[r] + rec.x);
-            t[r] = __vadd2(r == 0 ? diag_in : Hl[r - 1], S);
-          }
-          uint32_t F = fin;
-          uint32_t wd[RW];
-#pragma unroll
-          for (int kk = 0; kk < RW; kk++) { wd[kk] = 0; }
-
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            // the 8 flags of this row-step go to a register of their own (a short dependency chain
-            // per row instead of one 32-deep chain per word, which made ptxas park predicates in
-            // P2R/ISETP pairs); one multiply-add per row merges it into the output word
-            uint32_t fb = 0;
-            uint32_t const m1 = max_flag(t[r], F, fb, 1u, 16u);     // up:   F > h
-            uint32_t const h = max_flag(m1, E[r], fb, 2u, 32u);     // left: E > h
-            Hl[r] = h;
-            uint32_t const hf = h - rec.y;                          // H - QR_t
-            uint32_t const f = F - rec.z;                           // F - R_t
-            F = max_flag(hf, f, fb, 4u, 64u);                       // extup:   f > hf
-            uint32_t const he = h - QRq[r];
-            uint32_t const e = E[r] - Rq[r];
-            E[r] = max_flag(he, e, fb, 8u, 128u);                   // extleft: e > he
-            wd[r >> 2] = fb * (1u << (8u * (r & 3))) + wd[r >> 2];
-          }
-          Hout = Hl[R - 1];
-          Fout = F;
-          diag_in = hin;
-
-          if (RW == 1) { dptr[0] = wd[0]; }
-          else if (RW == 2) { *reinterpret_cast<uint2 *>(dptr) = make_uint2(wd[0], wd[1]); }
-          else { *reinterpret_cast<uint4 *>(dptr) = make_uint4(wd[0], wd[1], wd[RW > 2 ? 2 : 0], wd[RW > 3 ? 3 : 0]); }
-
-          if (write_bnd) { __stcg(mybnd + c, make_uint2(Hout, Fout)); }
-
-          if (capture && (c == Dlo - 1 || c == Dhi - 1)) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int r = 0; r < R; r++) { if (r == rlast) { v = Hl[r]; } }
-            if (c == Dlo - 1) { score_lo = static_cast<int>(v & 0xffffu) - static_cast<int>(BIAS); }
-            if (c == Dhi - 1) { score_hi = static_cast<int>(v >> 16) - static_cast<int>(BIAS); }
-          }
+      // this lane's records for the chunk start at column s0 - lane
+      uint32_t const slot0 = static_cast<uint32_t>(s0 - lane) & (RING - 1);
+      uint32_t aA = rA_s + slot0 * 16u, aB = rB_s + slot0 * 4u;
+      bool const steady = (s0 >= 32) && (s0 + 31 < dmax) &&
+                          (static_cast<unsigned>(cap_lo - s0) >= 32u) && (static_cast<unsigned>(cap_hi - s0) >= 32u);
+      if (steady) {
+#pragma unroll 2
+        for (int k = 0; k < 32; k++) {
+          step(std::false_type{}, s0 - lane + k, aA + k * 16u, aB + k * 4u, dptr + static_cast<size_t>(k) * 32 * RW);
+        }
+        dptr += 32 * 32 * RW;
+      } else {
+        int const kend = min(32, nsteps - s0);
+        int c = s0 - lane;
+        for (int k = 0; k < kend; k++, c++, aA += 16u, aB += 4u, dptr += 32 * RW) {
+          step(std::true_type{}, c, aA, aB, dptr);
         }
       }
     }

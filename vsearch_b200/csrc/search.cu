@@ -59,7 +59,27 @@ struct QState {
   int hit_count = 0, accepts = 0, rejects = 0, finalized = 0, delayed = 0;
   int gpos = -1;  // lazy mode: next hit of the open group to examine (-1: no group open)
   int gend = 0, greq = 0;  // lazy mode: end of the requested hit range, number of pairs requested
+  int cache_first = -1, cache_off = 0;  // tail mode: results of hits >= cache_first sit at tail cache[cache_off + x - cache_first]
   bool done = false, waiting = false;
+};
+
+struct SearchScratch {  // per host thread, see vsg_ctx::search_scratch
+  std::vector<uint32_t> h_seqno, h_count;
+  std::vector<int32_t> h_n;
+  std::vector<QState> st;
+  Hit * hits = nullptr;
+  size_t hits_cap = 0;
+  std::vector<uint32_t> pq, pt, lq, lt;
+  std::vector<int> pstate, px, lstate;
+  std::vector<int64_t> ldest;
+  std::vector<int16_t> a_score, l_score, t_score;
+  std::vector<uint16_t> a_al, a_ma, a_mi, a_ga, l_al, l_ma, l_mi, l_ga, t_al, t_ma, t_mi, t_ga;
+  std::vector<int32_t> a_tr, l_tr, t_tr;
+  std::vector<Hit> joined;
+  SearchScratch() = default;
+  SearchScratch(const SearchScratch &) = delete;
+  SearchScratch & operator=(const SearchScratch &) = delete;
+  ~SearchScratch() { std::free(hits); }
 };
 
 // align_trim's arithmetic (searchcore.cpp:409-463) from the first/last CIGAR run
@@ -179,6 +199,8 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   int nthreads = 8;
   if (const char * e = std::getenv("VSG_HOST_THREADS")) { nthreads = std::max(1, std::atoi(e)); }
   nthreads = static_cast<int>(std::min<int64_t>(nthreads, nbatches));
+  int64_t tail_pairs = 2048;  // a round with at most this many pairs starts the tail (0: never)
+  if (const char * e = std::getenv("VSG_TAIL_PAIRS")) { tail_pairs = std::max<int64_t>(0, std::atoll(e)); }
   while (static_cast<int>(c->children.size()) < nthreads) {
     vsg_ctx * ch = nullptr;
     int const r = vsg_ctx_create(c->device, &c->scoring, &ch);
@@ -191,18 +213,26 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   }
 
   vsg_ctx * const parent = c;
+  auto const t_call0 = std::chrono::steady_clock::now();
   auto run_batch = [&](vsg_ctx * c, int64_t b0, int64_t & total_pairs, int64_t & total_cells, int64_t & al_pairs, int64_t & al_cells) -> int {
-  std::vector<uint32_t> h_seqno, h_count;
-  std::vector<int32_t> h_n;
-  std::vector<QState> st;
-  Hit * hits = nullptr;  // bn*nstrands*tophits slots, deliberately uninitialised (each is zeroed when popped)
-  struct HitFree { Hit ** p; ~HitFree() { std::free(*p); } } hit_free{&hits};
-  std::vector<uint32_t> pq, pt;
-  std::vector<int> pstate;  // which state each pair belongs to
-  std::vector<int16_t> a_score;
-  std::vector<uint16_t> a_al, a_ma, a_mi, a_ga;
-  std::vector<int32_t> a_tr;
-  std::vector<Hit> joined;
+  // host buffers live in the worker's context: a batch touches ~20 MB of them, and fresh pages per
+  // batch (malloc -> mmap -> page faults) cost more than the bookkeeping itself
+  if (!c->search_scratch) { c->search_scratch = std::make_shared<SearchScratch>(); }
+  SearchScratch & sc = *static_cast<SearchScratch *>(c->search_scratch.get());
+  auto & h_seqno = sc.h_seqno; auto & h_count = sc.h_count; auto & h_n = sc.h_n; auto & st = sc.st;
+  Hit *& hits = sc.hits;  // bn*nstrands*tophits slots, deliberately uninitialised (each is zeroed when popped)
+  auto & pq = sc.pq; auto & pt = sc.pt;
+  auto & pstate = sc.pstate;  // which state each pair belongs to
+  auto & px = sc.px;          // which of the state's hits
+  // tail mode (see below): one device call resolves every remaining candidate of the few queries still active
+  auto & lq = sc.lq; auto & lt = sc.lt; auto & lstate = sc.lstate; auto & ldest = sc.ldest;
+  auto & l_score = sc.l_score; auto & t_score = sc.t_score;
+  auto & l_al = sc.l_al; auto & l_ma = sc.l_ma; auto & l_mi = sc.l_mi; auto & l_ga = sc.l_ga;
+  auto & t_al = sc.t_al; auto & t_ma = sc.t_ma; auto & t_mi = sc.t_mi; auto & t_ga = sc.t_ga;
+  auto & l_tr = sc.l_tr; auto & t_tr = sc.t_tr;
+  auto & a_score = sc.a_score; auto & a_al = sc.a_al; auto & a_ma = sc.a_ma; auto & a_mi = sc.a_mi; auto & a_ga = sc.a_ga;
+  auto & a_tr = sc.a_tr;
+  auto & joined = sc.joined;
   VSG_CUDA_OK(cudaSetDevice(c->device));
   static const bool trace = std::getenv("VSG_TRACE") != nullptr;
   auto now = []() { return std::chrono::steady_clock::now(); };
@@ -244,9 +274,15 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
     t_rank += ms(tp0, now()); tp0 = now();
     // one state per (query, strand); hits preallocated at tophits per state
     st.assign(static_cast<size_t>(bn) * nstrands, QState());
-    std::free(hits);
-    hits = static_cast<Hit *>(std::malloc(sizeof(Hit) * static_cast<size_t>(bn) * nstrands * tophits));
-    if (hits == nullptr) { Error::set("out of host memory"); return VSG_ENOMEM; }
+    {
+      size_t const need = static_cast<size_t>(bn) * nstrands * tophits;
+      if (need > sc.hits_cap) {
+        std::free(hits);
+        hits = static_cast<Hit *>(std::malloc(sizeof(Hit) * need));
+        sc.hits_cap = hits != nullptr ? need : 0;
+        if (hits == nullptr) { Error::set("out of host memory"); return VSG_ENOMEM; }
+      }
+    }
     for (int s = 0; s < nstrands; s++) {
       for (int64_t q = 0; q < bn; q++) {
         QState & S = st[static_cast<size_t>(s) * bn + q];
@@ -259,10 +295,11 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
 
     t_init += ms(tp0, now());
     bool any = true;
+    bool tail_mode = false;
     while (any) {
       tp0 = now();
       any = false;
-      pq.clear(); pt.clear(); pstate.clear();
+      pq.clear(); pt.clear(); pstate.clear(); px.clear();
       // gather: run each active query's candidate loop up to its next align_delayed (searchcore.cpp:915-954)
       if (lazy) {
         // same decisions, alignments on demand: open the group the reference would hand to search16,
@@ -312,6 +349,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
                 pq.push_back(static_cast<uint32_t>(strand == 0 ? q0 + b0 + ql : ql));
                 pt.push_back(static_cast<uint32_t>(h.target));
                 pstate.push_back(static_cast<int>(si));
+                px.push_back(x);
                 S.greq++;
               }
               S.gend = xend;
@@ -355,6 +393,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
             pq.push_back(static_cast<uint32_t>(strand == 0 ? q0 + b0 + ql : ql));
             pt.push_back(static_cast<uint32_t>(h.target));
             pstate.push_back(static_cast<int>(si));
+            px.push_back(x);
           }
         }
         S.waiting = true;
@@ -365,23 +404,84 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
       t_gather += ms(tp0, now()); tp0 = now();
       a_score.resize(np); a_al.resize(np); a_ma.resize(np); a_mi.resize(np); a_ga.resize(np); a_tr.resize(np * 4);
       // pairs of the plus strand index `queries`, those of the minus strand index rc_set: two calls
-      size_t split = np;
-      if (nstrands == 2) {
-        // states are ordered plus first, minus second, so pairs are too
-        split = 0;
-        while (split < np && static_cast<int64_t>(pstate[split]) < bn) { split++; }
-      }
-      for (int part = 0; part < 2; part++) {
-        size_t const lo = part == 0 ? 0 : split, hi = part == 0 ? split : np;
-        if (hi <= lo) { continue; }
-        const vsg_seqset * qset = part == 0 ? queries : rc_set;
-        int const r = vsg_align_pairs(c, qset, db, static_cast<int64_t>(hi - lo), pq.data() + lo, pt.data() + lo,
-                                      a_score.data() + lo, a_al.data() + lo, a_ma.data() + lo, a_mi.data() + lo,
-                                      a_ga.data() + lo, a_tr.data() + 4 * lo, nullptr, 0, nullptr);
+      // (states are ordered plus first, minus second, so pairs are too)
+      auto device_align = [&](size_t n, const uint32_t * Q, const uint32_t * T, const int * state_of,
+                              int16_t * o_sc, uint16_t * o_al, uint16_t * o_ma, uint16_t * o_mi, uint16_t * o_ga, int32_t * o_tr) -> int {
+        size_t split = n;
+        if (nstrands == 2) {
+          split = 0;
+          while (split < n && static_cast<int64_t>(state_of[split]) < bn) { split++; }
+        }
+        for (int part = 0; part < 2; part++) {
+          size_t const lo = part == 0 ? 0 : split, hi = part == 0 ? split : n;
+          if (hi <= lo) { continue; }
+          const vsg_seqset * qset = part == 0 ? queries : rc_set;
+          int const r = vsg_align_pairs(c, qset, db, static_cast<int64_t>(hi - lo), Q + lo, T + lo,
+                                        o_sc + lo, o_al + lo, o_ma + lo, o_mi + lo, o_ga + lo, o_tr + 4 * lo, nullptr, 0, nullptr);
+          if (r != VSG_OK) { return r; }
+        }
+        return VSG_OK;
+      };
+      bool const from_cache = tail_mode;
+      if (tail_mode) {
+        // every query still active had all its remaining candidates aligned when the tail began
+        for (size_t k = 0; k < np; k++) {
+          QState const & S = st[static_cast<size_t>(pstate[k])];
+          size_t const ci = static_cast<size_t>(S.cache_off + px[k] - S.cache_first);
+          a_score[k] = t_score[ci]; a_al[k] = t_al[ci]; a_ma[k] = t_ma[ci]; a_mi[k] = t_mi[ci]; a_ga[k] = t_ga[ci];
+          for (int z = 0; z < 4; z++) { a_tr[4 * k + z] = t_tr[4 * ci + z]; }
+        }
+      } else if (tail_pairs > 0 && np <= static_cast<size_t>(tail_pairs)) {
+        // TAIL: few queries are left and each would need up to five more rounds of eight candidates
+        // (searchcore.cpp:915-954), every round a device round trip with almost nothing in it.  Align
+        // all their remaining candidates now; later rounds replay from these results.  The decisions
+        // (and work[0..1], the reference's own pairs) are unchanged; work[2..3] include the extras.
+        lq.clear(); lt.clear(); lstate.clear(); ldest.clear();
+        int64_t ncache = 0;
+        for (size_t k = 0; k < np; k++) {
+          lq.push_back(pq[k]); lt.push_back(pt[k]); lstate.push_back(pstate[k]); ldest.push_back(static_cast<int64_t>(k));
+          if (k + 1 == np || pstate[k + 1] != pstate[k]) {
+            size_t const si = static_cast<size_t>(pstate[k]);
+            QState & S = st[si];
+            int const first_extra = lazy ? S.gend : S.hit_count;
+            int const strand = static_cast<int>(si / static_cast<size_t>(bn));
+            int64_t const ql = static_cast<int64_t>(si % static_cast<size_t>(bn));
+            int const sqlen = (strand == 0 ? queries->h_len[static_cast<size_t>(q0 + b0 + ql)] : rc_set->h_len[static_cast<size_t>(ql)]);
+            S.cache_first = first_extra; S.cache_off = static_cast<int>(ncache);
+            for (int idx = first_extra; idx < S.ncand; idx++) {
+              lq.push_back(pq[k]); lt.push_back(S.cs[idx]); lstate.push_back(pstate[k]); ldest.push_back(-(ncache + 1));
+              al_cells += static_cast<int64_t>(sqlen) * db->h_len[static_cast<size_t>(S.cs[idx])];
+              ncache++;
+            }
+          }
+        }
+        size_t const nl = lq.size();
+        l_score.resize(nl); l_al.resize(nl); l_ma.resize(nl); l_mi.resize(nl); l_ga.resize(nl); l_tr.resize(nl * 4);
+        size_t const nc = static_cast<size_t>(ncache);
+        t_score.resize(nc); t_al.resize(nc); t_ma.resize(nc); t_mi.resize(nc); t_ga.resize(nc); t_tr.resize(nc * 4);
+        int const r = device_align(nl, lq.data(), lt.data(), lstate.data(), l_score.data(), l_al.data(), l_ma.data(),
+                                   l_mi.data(), l_ga.data(), l_tr.data());
         if (r != VSG_OK) { if (rc_set) { vsg_seqset_destroy(rc_set); } return r; }
+        for (size_t k = 0; k < nl; k++) {
+          if (ldest[k] >= 0) {
+            size_t const d = static_cast<size_t>(ldest[k]);
+            a_score[d] = l_score[k]; a_al[d] = l_al[k]; a_ma[d] = l_ma[k]; a_mi[d] = l_mi[k]; a_ga[d] = l_ga[k];
+            for (int z = 0; z < 4; z++) { a_tr[4 * d + z] = l_tr[4 * k + z]; }
+          } else {
+            size_t const d = static_cast<size_t>(-ldest[k] - 1);
+            t_score[d] = l_score[k]; t_al[d] = l_al[k]; t_ma[d] = l_ma[k]; t_mi[d] = l_mi[k]; t_ga[d] = l_ga[k];
+            for (int z = 0; z < 4; z++) { t_tr[4 * d + z] = l_tr[4 * k + z]; }
+          }
+        }
+        al_pairs += static_cast<int64_t>(nl);
+        tail_mode = true;
+      } else {
+        int const r = device_align(np, pq.data(), pt.data(), pstate.data(), a_score.data(), a_al.data(), a_ma.data(),
+                                   a_mi.data(), a_ga.data(), a_tr.data());
+        if (r != VSG_OK) { if (rc_set) { vsg_seqset_destroy(rc_set); } return r; }
+        al_pairs += static_cast<int64_t>(np);
       }
       if (!lazy) { total_pairs += static_cast<int64_t>(np); }
-      al_pairs += static_cast<int64_t>(np);
       t_align += ms(tp0, now()); tp0 = now();
       // replay: the second half of align_delayed (searchcore.cpp:780-880)
       size_t pi = 0;
@@ -398,7 +498,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
           Hit & h = hits[static_cast<size_t>(S.hit_base) + x];
           if (!h.rejected) {
             int64_t const cl = static_cast<int64_t>(qlen) * db->h_len[static_cast<size_t>(h.target)];
-            al_cells += cl;
+            if (!from_cache) { al_cells += cl; }
             if (!lazy) { total_cells += cl; }
           }
         }
@@ -478,8 +578,8 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
     t_join += ms(tp0, now());
   }
   if (trace) {
-    std::fprintf(stderr, "[vsg trace] batch@%lld: rank %.1f init %.1f gather %.1f align %.1f replay %.1f join %.1f ms\n",
-                 static_cast<long long>(b0), t_rank, t_init, t_gather, t_align, t_replay, t_join);
+    std::fprintf(stderr, "[vsg trace] batch@%lld: rank %.1f init %.1f gather %.1f align %.1f replay %.1f join %.1f ms; done at %.1f ms\n",
+                 static_cast<long long>(b0), t_rank, t_init, t_gather, t_align, t_replay, t_join, ms(t_call0, now()));
   }
   return VSG_OK;
   };

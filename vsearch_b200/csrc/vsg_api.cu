@@ -391,38 +391,47 @@ extern "C" int64_t vsg_seqset_count(const vsg_seqset * s) { return s != nullptr 
 // ---- the aligner -----------------------------------------------------------------------------
 namespace {
 
-template <int R, bool G>
+template <int R, bool G, bool M>
 void launch_fast_one(vsg_ctx * c, const DevSeqs & qs, const DevSeqs & ts, const FastTask * d_tasks, int n)
 {
   int const blocks = (n + FAST_WARPS - 1) / FAST_WARPS;
-  nw_fast_kernel<R, G><<<blocks, FAST_WARPS * 32, 0, c->stream>>>(
+  constexpr size_t dyn = fast_dyn_smem(R, G);
+  if (dyn > 48 * 1024) {  // opt in to > 48 KB of dynamic shared memory (per device, cheap: set every time)
+    cudaFuncSetAttribute(nw_fast_kernel<R, G, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn));
+  }
+  nw_fast_kernel<R, G, M><<<blocks, FAST_WARPS * 32, dyn, c->stream>>>(
       c->sp, qs, ts, d_tasks, n, static_cast<uint8_t *>(c->dir.p), static_cast<uint2 *>(c->bnd.p),
       static_cast<int32_t *>(c->stats.p));
   count_launch();
 }
 
-void launch_fast(vsg_ctx * c, int R, bool general, const DevSeqs & qs, const DevSeqs & ts,
+// multi: the tasks' queries need more than one strip of 32*R rows (only possible for R > 8)
+void launch_fast(vsg_ctx * c, int R, bool general, bool multi, const DevSeqs & qs, const DevSeqs & ts,
                  const FastTask * d_tasks, int n)
 {
   if (general) {
     switch (R) {
-      case 4: launch_fast_one<4, true>(c, qs, ts, d_tasks, n); break;
-      case 8: launch_fast_one<8, true>(c, qs, ts, d_tasks, n); break;
-      default: launch_fast_one<16, true>(c, qs, ts, d_tasks, n); break;
+      case 4: launch_fast_one<4, true, false>(c, qs, ts, d_tasks, n); break;
+      case 8: launch_fast_one<8, true, false>(c, qs, ts, d_tasks, n); break;
+      default: launch_fast_one<16, true, true>(c, qs, ts, d_tasks, n); break;
     }
     return;
   }
   switch (R) {
-#define VSG_CASE(r) case r: launch_fast_one<r, false>(c, qs, ts, d_tasks, n); break;
+#define VSG_CASE(r) case r: launch_fast_one<r, false, false>(c, qs, ts, d_tasks, n); break;
     VSG_CASE(1) VSG_CASE(2) VSG_CASE(3) VSG_CASE(4) VSG_CASE(5) VSG_CASE(6) VSG_CASE(7) VSG_CASE(8)
+#undef VSG_CASE
+#define VSG_CASE(r) case r: if (multi) { launch_fast_one<r, false, true>(c, qs, ts, d_tasks, n); } \
+                            else { launch_fast_one<r, false, false>(c, qs, ts, d_tasks, n); } break;
     VSG_CASE(9) VSG_CASE(10) VSG_CASE(11) VSG_CASE(12) VSG_CASE(13) VSG_CASE(14) VSG_CASE(15)
-    default: launch_fast_one<16, false>(c, qs, ts, d_tasks, n); break;
+    default: if (multi) { launch_fast_one<16, false, true>(c, qs, ts, d_tasks, n); }
+             else { launch_fast_one<16, false, false>(c, qs, ts, d_tasks, n); } break;
 #undef VSG_CASE
   }
 }
 
 // A chunk = the tasks whose direction blocks share the scratch buffer at the same time.
-struct ClassRun { int R; bool general; size_t first; int count; };  // a run of one kernel class in all_fast
+struct ClassRun { int R; bool general, multi; size_t first; int count; };  // a run of one kernel class in all_fast
 struct ChunkPlan {
   std::vector<ClassRun> runs;
   size_t exact_first = 0; int exact_count = 0;
@@ -432,7 +441,7 @@ struct ChunkPlan {
 };
 
 struct ChunkBuilder {  // the chunk being filled
-  std::vector<FastTask> fast[2][FAST_RMAX + 1];
+  std::vector<FastTask> fast[2][2][FAST_RMAX + 1];  // [general][several strips][rows per lane]
   std::vector<ExactTask> exact;
   uint64_t dir_bytes = 0, bnd_elems = 0, he_elems = 0, cigar_bytes = 0;
   int64_t cells = 0, nfast = 0, nexact = 0;
@@ -495,14 +504,15 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
   auto close_chunk = [&]() {
     if (cb.empty()) { return; }
     ChunkPlan pl;
-    for (int g = 0; g < 2; g++) {
+    for (int gm = 0; gm < 4; gm++) {
+      int const g = gm >> 1, m = gm & 1;
       for (int R = 1; R <= FAST_RMAX; R++) {
-        auto & v = cb.fast[g][R];
+        auto & v = cb.fast[g][m][R];
         if (v.empty()) { continue; }
         // longest first: the tail of the grid is made of the short ones
         auto const longer = [](const FastTask & a, const FastTask & b) { return a.dmax > b.dmax; };
         if (!std::is_sorted(v.begin(), v.end(), longer)) { std::sort(v.begin(), v.end(), longer); }
-        pl.runs.push_back(ClassRun{R, g != 0, all_fast.size(), static_cast<int>(v.size())});
+        pl.runs.push_back(ClassRun{R, g != 0, m != 0, all_fast.size(), static_cast<int>(v.size())});
         all_fast.insert(all_fast.end(), v.begin(), v.end());
         v.clear();
       }
@@ -606,7 +616,7 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
         if (pair2) { add_pairdesc(q, b.t, 0, b.slot, R, 1, dmax, cb.dir_bytes); }
         cb.dir_bytes += dirb;
         if (ns > 1) { cb.bnd_elems += static_cast<uint64_t>(dmax); }
-        cb.fast[a.general ? 1 : 0][R].push_back(ft);
+        cb.fast[a.general ? 1 : 0][ns > 1 ? 1 : 0][R].push_back(ft);
         cb.cells += static_cast<int64_t>(Q) * a.d + (pair2 ? static_cast<int64_t>(Q) * b.d : 0);
         cb.nfast += pair2 ? 2 : 1;
         k += pair2 ? 2 : 1;
@@ -656,7 +666,7 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
   for (size_t ci = 0; ci < plans.size(); ci++) {
     ChunkPlan const & pl = plans[ci];
     VSG_CUDA_OK(cudaEventRecord(c->ev_pool[3 * ci], c->stream));
-    for (auto const & run : pl.runs) { launch_fast(c, run.R, run.general, queries->d, targets->d, d_fast + run.first, run.count); }
+    for (auto const & run : pl.runs) { launch_fast(c, run.R, run.general, run.multi, queries->d, targets->d, d_fast + run.first, run.count); }
     if (pl.exact_count > 0) {
       nw_exact_kernel<<<(pl.exact_count + 63) / 64, 64, 0, c->stream>>>(sp, queries->d, targets->d, d_exact + pl.exact_first,
                                                                         pl.exact_count, d_dir, static_cast<int16_t *>(c->he.p), d_stats);

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -128,4 +129,5 @@ struct vsg_ctx {
   vsg_fallback_fn fallback = nullptr;  // host-side aligner for SHRT_MAX pairs
   void * fallback_user = nullptr;
   std::vector<vsg_ctx *> children;  // per-host-thread contexts of vsg_search_batch
+  std::shared_ptr<void> search_scratch;  // host buffers of vsg_search_batch's driver, kept between calls
 };
