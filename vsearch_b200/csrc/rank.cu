@@ -163,7 +163,7 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
   uint32_t * const kmers = counters + COUNTER_WORDS + 3;                          // KMER_CAP
   uint32_t * const lbeg = kmers + KMER_CAP;                                       // KMER_CAP
   uint32_t * const llen = lbeg + KMER_CAP;                                        // KMER_CAP
-  __shared__ int s_ncand, s_nk;
+  __shared__ int s_ncand, s_nk, s_T, s_K;
   __shared__ int s_wsum[RANK_THREADS / 32];
 
   int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -229,6 +229,36 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
     }
     // search_topscores: count >= min(minwordmatches, kmersamplecount)  (searchcore.cpp:320)
     uint32_t const minmatches = static_cast<uint32_t>(minwordmatches < nk ? minwordmatches : nk);
+    // RUNNING THRESHOLD (queries with np2 + nk + 1 <= KMER_CAP, i.e. up to ~1000 nt): hist[c] counts,
+    // over the shards seen so far, the targets whose k-mer count is c; T = the largest count with at
+    // least `tophits` targets at or above it.  A target below T can never reach the final list, so
+    // only counts >= T are turned into candidate keys: a few dozen per shard instead of the ~3 % of
+    // all targets that pass the reference's fixed threshold (searchcore.cpp:320), no overflow sorts.
+    bool const running = !longq && (np2 + nk + 1 <= KMER_CAP);
+    uint32_t * const hist = kmers + np2;  // nk + 1 bins in the unused tail of the k-mer array
+    if (running) {
+      for (int i = threadIdx.x; i <= nk; i += blockDim.x) { hist[i] = 0; }
+      if (threadIdx.x == 0) { s_T = static_cast<int>(minmatches); }
+    }
+    // visits every counter >= thr of the current shard: f(count, local target)
+    auto scan_counters = [&](int nt, uint32_t thr, auto && f) {
+      int const nvec = (((nt + 1) >> 1) + 3) >> 2;
+      uint32_t const below = thr > 0 ? ((thr - 1) | ((thr - 1) << 16)) : 0u;
+      const uint4 * __restrict__ cv = reinterpret_cast<const uint4 *>(counters);
+      for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+        uint4 const x = cv[vi];
+        uint32_t const w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          // some half above thr-1?  (thr == 0: everything passes)
+          if (thr > 0 && __vmaxu2(w[u], below) == below) { continue; }
+          uint32_t const c0 = w[u] & 0xffffu, c1 = w[u] >> 16;
+          int const lt0 = 2 * (4 * vi + u), lt1 = lt0 + 1;
+          if (c0 >= thr && lt0 < nt) { f(c0, lt0); }
+          if (c1 >= thr && lt1 < nt) { f(c1, lt1); }
+        }
+      }
+    };
 
     for (int sh = 0; sh < nshards; sh++) {
       ShardDev const S = shards[sh];
@@ -307,10 +337,51 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
       }
       __syncthreads();
       }  // chunk
+      int const nwords = (S.nt + 1) >> 1;
+      uint32_t thr = minmatches;
+      if (running) {
+        // 4r. histogram of this shard's counts >= T, new T, then keys for counts >= new T only
+        uint32_t const T0 = static_cast<uint32_t>(s_T);
+        scan_counters(S.nt, T0, [&](uint32_t c, int) { atomicAdd(&hist[c], 1u); });
+        __syncthreads();
+        if (warp == 0) {
+          int acc = 0, T = static_cast<int>(T0), K = -1;
+          for (int top = nk; top >= static_cast<int>(T0); top -= 32) {
+            int const b = top - lane;
+            int v = b >= static_cast<int>(T0) ? static_cast<int>(hist[b]) : 0;
+            // inclusive prefix over lanes = suffix over bins (lane 0 is the highest bin)
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int const o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) { v += o; } }
+            unsigned const hit = __ballot_sync(0xffffffffu, acc + v >= tophits);
+            if (hit != 0u) {
+              int const first = __ffs(hit) - 1;
+              T = top - first;
+              K = acc + __shfl_sync(0xffffffffu, v, first);
+              break;
+            }
+            acc += __shfl_sync(0xffffffffu, v, 31);
+          }
+          if (K < 0) { K = acc; }  // fewer than tophits targets so far: keep them all
+          if (lane == 0) { s_T = T; s_K = K; }
+        }
+        int const level = s_ncand;
+        __syncthreads();
+        uint32_t const T1 = static_cast<uint32_t>(s_T);
+        int const K = s_K;
+        if (level + K <= CAND_CAP) {
+          // at most K targets (all shards so far) are >= T1, so at most K keys are appended here
+          scan_counters(S.nt, T1, [&](uint32_t c, int lt) {
+            int const t = S.t0 + lt;
+            cand[atomicAdd(&s_ncand, 1)] = make_key(c, static_cast<uint32_t>(db.len[t]), static_cast<uint32_t>(t));
+          });
+          __syncthreads();
+          continue;  // next shard
+        }
+        thr = T1;  // a crowd of ties at T1: the sort-and-cut path below, from T1 up
+      } else {
       // 4. threshold scan.  Common case: count the survivors, one block-wide prefix sum, write them
       //    straight to their slots (no barrier per segment).  Only if they would not fit does the
       //    segmented sort-and-cut path below run.
-      int const nwords = (S.nt + 1) >> 1;
       {
         int mycount = 0;
         for (int wi = threadIdx.x; wi < nwords; wi += blockDim.x) {
@@ -346,6 +417,7 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
           continue;  // next shard
         }
       }
+      }
       // 4b. segmented scan with sort-and-cut when the candidate list could overflow
       for (int seg = 0; seg < nwords; seg += SCAN_SEG_WORDS) {
         // every thread must take the same decision: read the fill level, then fence the read off
@@ -365,11 +437,11 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
           uint32_t const w = counters[wi];
           uint32_t const c0 = w & 0xffffu, c1 = w >> 16;
           int const lt0 = 2 * wi, lt1 = 2 * wi + 1;
-          if (c0 >= minmatches && lt0 < S.nt) {
+          if (c0 >= thr && lt0 < S.nt) {
             int const t = S.t0 + lt0;
             cand[atomicAdd(&s_ncand, 1)] = make_key(c0, static_cast<uint32_t>(db.len[t]), static_cast<uint32_t>(t));
           }
-          if (c1 >= minmatches && lt1 < S.nt) {
+          if (c1 >= thr && lt1 < S.nt) {
             int const t = S.t0 + lt1;
             cand[atomicAdd(&s_ncand, 1)] = make_key(c1, static_cast<uint32_t>(db.len[t]), static_cast<uint32_t>(t));
           }
@@ -381,7 +453,21 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
     //    count T of the tophits-th best with a histogram, keep count >= T, sort only those.
     int m = s_ncand;
     __syncthreads();
-    if (m > 2 * tophits && nk + 1 <= 2 * KMER_CAP) {
+    if (running) {
+      if (m > 2 * tophits) {
+        // keys below the final T were appended while T was still lower: drop them before sorting
+        uint64_t const tkey = static_cast<uint64_t>(static_cast<uint32_t>(s_T)) << 49;
+        uint64_t mine[CAND_CAP / RANK_THREADS];
+        int cnt = 0;
+        for (int i = threadIdx.x; i < m; i += blockDim.x) { uint64_t const kx = cand[i]; if (kx >= tkey) { mine[cnt++] = kx; } }
+        if (threadIdx.x == 0) { s_ncand = 0; }
+        __syncthreads();
+        int base = cnt > 0 ? atomicAdd(&s_ncand, cnt) : 0;
+        for (int i = 0; i < cnt; i++) { cand[base + i] = mine[i]; }
+        __syncthreads();
+        m = s_ncand;
+      }
+    } else if (m > 2 * tophits && nk + 1 <= 2 * KMER_CAP) {
       uint32_t * const hist = lbeg;  // 2 * KMER_CAP words available, counts are <= nk <= KMER_CAP
       int const nb = nk + 1;
       for (int i = threadIdx.x; i < nb; i += blockDim.x) { hist[i] = 0; }

@@ -199,7 +199,9 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   int nthreads = 8;
   if (const char * e = std::getenv("VSG_HOST_THREADS")) { nthreads = std::max(1, std::atoi(e)); }
   nthreads = static_cast<int>(std::min<int64_t>(nthreads, nbatches));
-  int64_t tail_pairs = 2048;  // a round with at most this many pairs starts the tail (0: never)
+  bool stagger = true;
+  if (const char * e = std::getenv("VSG_STAGGER")) { stagger = std::atoi(e) != 0; }
+  int64_t tail_pairs = 4096;  // the tail starts when the round's pairs + all remaining candidates fit in this (0: never)
   if (const char * e = std::getenv("VSG_TAIL_PAIRS")) { tail_pairs = std::max<int64_t>(0, std::atoll(e)); }
   while (static_cast<int>(c->children.size()) < nthreads) {
     vsg_ctx * ch = nullptr;
@@ -214,7 +216,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
 
   vsg_ctx * const parent = c;
   auto const t_call0 = std::chrono::steady_clock::now();
-  auto run_batch = [&](vsg_ctx * c, int64_t b0, int64_t & total_pairs, int64_t & total_cells, int64_t & al_pairs, int64_t & al_cells) -> int {
+  auto run_batch = [&](vsg_ctx * c, int64_t b0, int64_t bn_req, int64_t & total_pairs, int64_t & total_cells, int64_t & al_pairs, int64_t & al_cells) -> int {
   // host buffers live in the worker's context: a batch touches ~20 MB of them, and fresh pages per
   // batch (malloc -> mmap -> page faults) cost more than the bookkeeping itself
   if (!c->search_scratch) { c->search_scratch = std::make_shared<SearchScratch>(); }
@@ -243,7 +245,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   auto tp0 = now();
   {
 
-    int64_t const bn = std::min(BATCH, nq - b0);
+    int64_t const bn = std::min(bn_req, nq - b0);
     vsg_seqset * rc_set = nullptr;
     if (nstrands == 2) {
       int const r = seqset_revcomp(c, queries, q0 + b0, bn, &rc_set);
@@ -423,6 +425,17 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
         return VSG_OK;
       };
       bool const from_cache = tail_mode;
+      // what the tail shortcut would add to this round: every candidate the active queries have left
+      auto count_extras = [&]() -> size_t {
+        size_t extras = 0;
+        for (size_t k = 0; k < np; k++) {
+          if (k + 1 == np || pstate[k + 1] != pstate[k]) {
+            QState const & S = st[static_cast<size_t>(pstate[k])];
+            extras += static_cast<size_t>(std::max(0, S.ncand - (lazy ? S.gend : S.hit_count)));
+          }
+        }
+        return extras;
+      };
       if (tail_mode) {
         // every query still active had all its remaining candidates aligned when the tail began
         for (size_t k = 0; k < np; k++) {
@@ -431,7 +444,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
           a_score[k] = t_score[ci]; a_al[k] = t_al[ci]; a_ma[k] = t_ma[ci]; a_mi[k] = t_mi[ci]; a_ga[k] = t_ga[ci];
           for (int z = 0; z < 4; z++) { a_tr[4 * k + z] = t_tr[4 * ci + z]; }
         }
-      } else if (tail_pairs > 0 && np <= static_cast<size_t>(tail_pairs)) {
+      } else if (tail_pairs > 0 && np <= static_cast<size_t>(tail_pairs) && np + count_extras() <= static_cast<size_t>(tail_pairs)) {
         // TAIL: few queries are left and each would need up to five more rounds of eight candidates
         // (searchcore.cpp:915-954), every round a device round trip with almost nothing in it.  Align
         // all their remaining candidates now; later rounds replay from these results.  The decisions
@@ -590,11 +603,19 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   std::vector<int64_t> tp(static_cast<size_t>(nthreads), 0), tc(static_cast<size_t>(nthreads), 0), ap(static_cast<size_t>(nthreads), 0), ac(static_cast<size_t>(nthreads), 0);
   auto worker = [&](int t) {
     vsg_ctx * wc = c->children[static_cast<size_t>(t)];
+    // Sub-batches are cut from a shared cursor.  A thread's FIRST one is shortened to (t+1)/nthreads of
+    // the regular size: identical sub-batches started together run in lockstep (all threads rank, then
+    // all gather on the host, then all align ...) and the device idles through every host phase;
+    // staggered, some thread always has a kernel in flight.
+    bool first = true;
     for (;;) {
-      int64_t const bi = next.fetch_add(1);
-      if (bi >= nbatches) { break; }
-      int const r = run_batch(wc, bi * BATCH, tp[static_cast<size_t>(t)], tc[static_cast<size_t>(t)], ap[static_cast<size_t>(t)], ac[static_cast<size_t>(t)]);
-      if (r != VSG_OK) { rcs[static_cast<size_t>(t)] = r; msgs[static_cast<size_t>(t)] = vsg_last_error(); next.store(nbatches); break; }
+      int64_t want = BATCH;
+      if (first && stagger && nthreads > 1) { want = std::max<int64_t>(256, BATCH * (t + 1) / nthreads); }
+      first = false;
+      int64_t const b0 = next.fetch_add(want);
+      if (b0 >= nq) { break; }
+      int const r = run_batch(wc, b0, want, tp[static_cast<size_t>(t)], tc[static_cast<size_t>(t)], ap[static_cast<size_t>(t)], ac[static_cast<size_t>(t)]);
+      if (r != VSG_OK) { rcs[static_cast<size_t>(t)] = r; msgs[static_cast<size_t>(t)] = vsg_last_error(); next.store(nq); break; }
     }
   };
   if (nthreads == 1) {
