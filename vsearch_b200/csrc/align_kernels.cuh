@@ -45,6 +45,16 @@ constexpr int FAST_RMAX = 16;        // rows per lane
 constexpr int RING = 64;             // column records per warp
 
 __host__ __device__ inline int fast_rw(int R) { return R <= 4 ? 1 : (R <= 8 ? 2 : 4); }
+// Direction bytes of one strip.  Layout: a lane's direction words of 4/RW consecutive wavefront
+// steps form one 16-byte TILE (RW = 1: four steps, RW = 2: two, RW = 4: one); the tiles of the 32
+// lanes of a step group lie back to back, so the warp writes a group with one fully coalesced
+// 512-byte store.  A diagonal move of the traceback (one row up = same lane one byte down, one
+// column left = one step back) stays inside the tile, which the traceback keeps in registers:
+// one 16-byte load serves up to 4/RW steps of the walk.
+__host__ __device__ inline size_t fast_strip_bytes(int dmax, int R)
+{
+  return static_cast<size_t>((dmax + 31 + 3) & ~3) * 32 * fast_rw(R) * 4;
+}
 
 __device__ __forceinline__ uint32_t pk2(int lo, int hi)
 {
@@ -154,7 +164,7 @@ nw_fast_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
   int const nsteps = dmax + 31;
   int const strip_rows = 32 * R;
   int const nstrips = MULTI ? (Q + strip_rows - 1) / strip_rows : 1;
-  size_t const strip_bytes = static_cast<size_t>(nsteps) * 32 * RW * 4;
+  size_t const strip_bytes = fast_strip_bytes(dmax, R);
 
   int const QRqi = sp.go[Q_I] + sp.ge[Q_I], Rqi = sp.ge[Q_I];
   int const QRqr = sp.go[Q_R] + sp.ge[Q_R], Rqr = sp.ge[Q_R];
@@ -238,7 +248,8 @@ nw_fast_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
     // one step of the wavefront: this lane's R rows of column c.  EDGE steps may find the lane
     // outside the matrix (ramp-up / ramp-down) and may have to pick up the final score; steady
     // steps (all 32 lanes inside, no score to capture) skip those tests.
-    auto step = [&](auto edge_tag, int c, uint32_t aA, uint32_t aB, uint32_t * dptr) {
+    struct Words { uint32_t v[RW]; };  // the direction words one lane produces in one step
+    auto step = [&](auto edge_tag, int c, uint32_t aA, uint32_t aB, Words & out) -> bool {
       constexpr bool EDGE = decltype(edge_tag)::value;
       uint32_t hin = __shfl_up_sync(0xffffffffu, Hout, 1);
       uint32_t fin = __shfl_up_sync(0xffffffffu, Fout, 1);
@@ -294,9 +305,8 @@ nw_fast_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
         Fout = F;
         diag_in = hin;
 
-        if (RW == 1) { dptr[0] = wd[0]; }
-        else if (RW == 2) { *reinterpret_cast<uint2 *>(dptr) = make_uint2(wd[0], wd[1]); }
-        else { *reinterpret_cast<uint4 *>(dptr) = make_uint4(wd[0], wd[1], wd[RW > 2 ? 2 : 0], wd[RW > 3 ? 3 : 0]); }
+#pragma unroll
+        for (int kk = 0; kk < RW; kk++) { out.v[kk] = wd[kk]; }
 
         if (MULTI && write_bnd) { __stcg(mybnd + c, make_uint2(Hout, Fout)); }
 
@@ -307,10 +317,14 @@ nw_fast_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
           if (c == Dlo - 1) { score_lo = static_cast<int>(v & 0xffffu) - static_cast<int>(BIAS); }
           if (c == Dhi - 1) { score_hi = static_cast<int>(v >> 16) - static_cast<int>(BIAS); }
         }
+        return true;
       }
+      return false;
     };
 
-    uint32_t * dptr = reinterpret_cast<uint32_t *>(dstrip) + static_cast<size_t>(lane) * RW;
+    // the tile this lane writes for steps [g*SPT, g*SPT + SPT) starts at dwords + g * 128
+    constexpr int SPT = 4 / RW;
+    uint32_t * const dwords = reinterpret_cast<uint32_t *>(dstrip) + static_cast<size_t>(lane) * 4;
     for (int s0 = 0; s0 < nsteps; s0 += 32) {
       {
         // refill the ring with columns [s0, s0+32): one column per lane, coalesced
@@ -347,16 +361,35 @@ nw_fast_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
       bool const steady = (s0 >= 32) && (s0 + 31 < dmax) &&
                           (static_cast<unsigned>(cap_lo - s0) >= 32u) && (static_cast<unsigned>(cap_hi - s0) >= 32u);
       if (steady) {
-#pragma unroll 2
-        for (int k = 0; k < 32; k++) {
-          step(std::false_type{}, s0 - lane + k, aA + k * 16u, aB + k * 4u, dptr + static_cast<size_t>(k) * 32 * RW);
+        constexpr int UNR = (RW == 1) ? 4 : 2;  // steps per trip: a whole tile (RW <= 2) or two (RW == 4)
+#pragma unroll 1
+        for (int k0 = 0; k0 < 32; k0 += UNR) {
+          Words b[UNR];
+#pragma unroll
+          for (int u = 0; u < UNR; u++) {
+            step(std::false_type{}, s0 - lane + k0 + u, aA + (k0 + u) * 16u, aB + (k0 + u) * 4u, b[u]);
+          }
+          uint4 * const tp = reinterpret_cast<uint4 *>(dwords + static_cast<size_t>((s0 + k0) / SPT) * 128);
+          if (RW == 1) { tp[0] = make_uint4(b[0].v[0], b[1].v[0], b[UNR > 2 ? 2 : 0].v[0], b[UNR > 3 ? 3 : 0].v[0]); }
+          else if (RW == 2) { tp[0] = make_uint4(b[0].v[0], b[0].v[1], b[1].v[0], b[1].v[1]); }
+          else {
+#pragma unroll
+            for (int u = 0; u < UNR; u++) { tp[32 * u] = make_uint4(b[u].v[0], b[u].v[1], b[u].v[RW > 2 ? 2 : 0], b[u].v[RW > 3 ? 3 : 0]); }
+          }
         }
-        dptr += 32 * 32 * RW;
       } else {
         int const kend = min(32, nsteps - s0);
         int c = s0 - lane;
-        for (int k = 0; k < kend; k++, c++, aA += 16u, aB += 4u, dptr += 32 * RW) {
-          step(std::true_type{}, c, aA, aB, dptr);
+        for (int k = 0; k < kend; k++, c++, aA += 16u, aB += 4u) {
+          Words w1;
+          if (step(std::true_type{}, c, aA, aB, w1)) {
+            uint32_t const * const wd = w1.v;
+            int const sg = s0 + k;
+            uint32_t * const dp = dwords + static_cast<size_t>(sg / SPT) * 128 + (sg % SPT) * RW;
+            if (RW == 1) { dp[0] = wd[0]; }
+            else if (RW == 2) { *reinterpret_cast<uint2 *>(dp) = make_uint2(wd[0], wd[1]); }
+            else { *reinterpret_cast<uint4 *>(dp) = make_uint4(wd[0], wd[1], wd[RW > 2 ? 2 : 0], wd[RW > 3 ? 3 : 0]); }
+          }
         }
       }
     }
@@ -478,17 +511,61 @@ struct DirReader {
   int kind, R, RW, half, D;
   size_t strip_bytes;
   int strip_rows;
-  __device__ __forceinline__ int get(int i, int j) const
+  // position of the current row i, kept incrementally (the walk only ever moves one row up)
+  int l = 0, r = 0, sh = 0;        // fast layout: lane, row within the lane, log2(steps per tile)
+  size_t row_base = 0;             // fast: strip offset; exact: i * D
+  // the 16-byte tile read last (fast layout): consecutive traceback steps mostly stay inside it
+  size_t tile_at = ~static_cast<size_t>(0);
+  uint4 tile = {0u, 0u, 0u, 0u};
+  __device__ __forceinline__ void start(int i)
   {
-    if (kind == 1) { return base[static_cast<size_t>(i) * D + j]; }
+    if (kind == 1) { row_base = static_cast<size_t>(i) * D; return; }
     int const strip = i / strip_rows;
     int const il = i - strip * strip_rows;
-    int const l = il / R;
-    int const r = il - l * R;
-    size_t const a = static_cast<size_t>(strip) * strip_bytes +
-                     (static_cast<size_t>(j + l) * 32 + l) * (RW * 4) + r;
-    int const v = base[a];
+    l = il / R;
+    r = il - l * R;
+    row_base = static_cast<size_t>(strip) * strip_bytes;
+    sh = RW == 1 ? 2 : (RW == 2 ? 1 : 0);
+  }
+  __device__ __forceinline__ void up()  // i -> i - 1
+  {
+    if (kind == 1) { row_base -= static_cast<size_t>(D); return; }
+    if (--r < 0) {
+      r = R - 1;
+      if (--l < 0) { l = 31; row_base -= strip_bytes; }
+    }
+  }
+  __device__ __forceinline__ int get(int j)
+  {
+    if (kind == 1) { return base[row_base + j]; }
+    int const sg = j + l;  // wavefront step at which lane l visits column j
+    int const g = sg >> sh;
+    size_t const a = row_base + (static_cast<size_t>(g) * 32 + l) * 16;
+    if (a != tile_at) {
+      tile = __ldg(reinterpret_cast<const uint4 *>(base + a));
+      tile_at = a;
+    }
+    int const idx = (sg - (g << sh)) * (RW * 4) + r;  // byte within the tile
+    int const wsel = idx >> 2;
+    uint32_t const w = wsel == 0 ? tile.x : (wsel == 1 ? tile.y : (wsel == 2 ? tile.z : tile.w));
+    int const v = static_cast<int>((w >> (8 * (idx & 3))) & 0xffu);
     return half ? (v >> 4) : (v & 15);
+  }
+};
+
+// four sequence symbols at a time for the traceback's backward walk (a thread's loads are not
+// coalesced with its neighbours': every load instruction costs the warp 32 memory transactions)
+struct SymCache {
+  uintptr_t at = 0;  // address of the aligned 4-byte word held
+  uint32_t w = 0;
+  __device__ __forceinline__ int get(uint8_t const * __restrict__ p, int i)
+  {
+    // the aligned word around p[i] lies inside the symbol buffer's allocation (device allocations
+    // start and end on coarser boundaries than 4 bytes)
+    uintptr_t const a = reinterpret_cast<uintptr_t>(p + i);
+    uintptr_t const wa = a & ~static_cast<uintptr_t>(3);
+    if (wa != at) { at = wa; w = __ldg(reinterpret_cast<const uint32_t *>(wa)); }
+    return static_cast<int>((w >> (8 * (a & 3))) & 15u);
   }
 };
 
@@ -541,11 +618,12 @@ __device__ __forceinline__ void traceback_one(const ScoreParams & sp, const DevS
   uint8_t const * __restrict__ qsym = qs.sym + qs.off[pd.q];
   uint8_t const * __restrict__ dsym = ts.sym + ts.off[pd.t];
 
+  SymCache qc, tc;
   DirReader rd;
   rd.base = dir + pd.dir_off;
   rd.kind = pd.kind; rd.R = pd.R; rd.RW = fast_rw(pd.R); rd.half = pd.half; rd.D = D;
   rd.strip_rows = 32 * pd.R;
-  rd.strip_bytes = static_cast<size_t>(pd.dmax + 31) * 32 * rd.RW * 4;
+  rd.strip_bytes = fast_strip_bytes(pd.dmax, pd.R);
 
   CigarWriter cw;
   cw.text = TEXT;
@@ -555,6 +633,7 @@ __device__ __forceinline__ void traceback_one(const ScoreParams & sp, const DevS
 
   int aligned = 0, matches = 0, mismatches = 0, gaps = 0;
   int i = Q - 1, j = D - 1;
+  rd.start(i);
   char op = 0;
   int last_run_op = 0;  // op of the run that ends the alignment (first one pushed)
   int last_run = 0;
@@ -562,18 +641,18 @@ __device__ __forceinline__ void traceback_one(const ScoreParams & sp, const DevS
 
   while (i >= 0 && j >= 0) {
     aligned++;
-    int const b = rd.get(i, j);
+    int const b = rd.get(j);
     char nop;
     if (op == 'I' && (b & 8)) { j--; nop = 'I'; }
-    else if (op == 'D' && (b & 4)) { i--; nop = 'D'; }
+    else if (op == 'D' && (b & 4)) { i--; rd.up(); nop = 'D'; }
     else if (b & 2) { if (op != 'I') { gaps++; } j--; nop = 'I'; }
-    else if (b & 1) { if (op != 'D') { gaps++; } i--; nop = 'D'; }
+    else if (b & 1) { if (op != 'D') { gaps++; } i--; rd.up(); nop = 'D'; }
     else {
-      int const a = qsym[i] & 15, c = dsym[j] & 15;
+      int const a = qc.get(qsym, i), c = tc.get(dsym, j);
       if ((a & c) != 0) {
         if (sp.n_mismatch && (a == 15 || c == 15)) { mismatches++; } else { matches++; }
       } else { mismatches++; }
-      i--; j--; nop = 'M';
+      i--; j--; rd.up(); nop = 'M';
     }
     if (first_run_open) {
       if (last_run == 0 || nop == last_run_op) { last_run_op = nop; last_run++; }

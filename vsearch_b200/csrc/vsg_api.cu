@@ -603,7 +603,7 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
         int R, ns;
         fast_shape(Q, a.general, R, ns);
         int const dmax = std::max(a.d, b.d);
-        uint64_t const dirb = static_cast<uint64_t>(ns) * (dmax + 31) * 32 * fast_rw(R) * 4;
+        uint64_t const dirb = static_cast<uint64_t>(ns) * fast_strip_bytes(dmax, R);
         if (!cb.empty() && cb.dir_bytes + dirb > c->dir_budget) { close_chunk(); }
         FastTask ft{};
         ft.q = q; ft.tlo = a.t; ft.thi = b.t;
