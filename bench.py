@@ -417,7 +417,7 @@ def main():
                    "source": "profiles/nw_fast_r01.ncu-rep"}
     except Exception:
         pass
-    roofline = {"bound": "int_alu", "kernel": "nw_fast_kernel<8,false>",
+    roofline = {"bound": "int_alu", "kernel": "nw_fast_kernel<8,false,false>",
                 "achieved": fwd_gcups, "peak": int_peak_gcups, "unit": "GCUPS", "frac": fwd_gcups / int_peak_gcups,
                 "peak_source": "vsg_measure_int_peak (VIMNMX.S16x2+VIADD.16x2 lane-ops/s, measured live, burst) x2 cells /15 ops",
                 "packed_lane_ops_per_s": peak_ops,

@@ -594,7 +594,7 @@ struct CigarWriter {
   __device__ __forceinline__ void push(char o)
   {
     if (o == op) { run++; return; }
-    flush();
+    if (text) { flush(); }  // statistics-only walks need the open run (op, run), not the text length
     op = o;
     run = 1;
   }
@@ -642,18 +642,23 @@ __device__ __forceinline__ void traceback_one(const ScoreParams & sp, const DevS
   while (i >= 0 && j >= 0) {
     aligned++;
     int const b = rd.get(j);
-    char nop;
-    if (op == 'I' && (b & 8)) { j--; nop = 'I'; }
-    else if (op == 'D' && (b & 4)) { i--; rd.up(); nop = 'D'; }
-    else if (b & 2) { if (op != 'I') { gaps++; } j--; nop = 'I'; }
-    else if (b & 1) { if (op != 'D') { gaps++; } i--; rd.up(); nop = 'D'; }
-    else {
+    // backtrack16's priorities (align_simd.cpp:1150-1190) as selects: the lanes of a warp walk
+    // unrelated alignments, so every branch here is a divergent one
+    bool const ext_i = (op == 'I') && (b & 8);
+    bool const ext_d = !ext_i && (op == 'D') && (b & 4);
+    bool const open_i = !ext_i && !ext_d && (b & 2);
+    bool const open_d = !ext_i && !ext_d && !open_i && (b & 1);
+    bool const is_i = ext_i || open_i, is_d = ext_d || open_d;
+    gaps += ((open_i && op != 'I') || (open_d && op != 'D')) ? 1 : 0;
+    if (!is_i && !is_d) {
       int const a = qc.get(qsym, i), c = tc.get(dsym, j);
-      if ((a & c) != 0) {
-        if (sp.n_mismatch && (a == 15 || c == 15)) { mismatches++; } else { matches++; }
-      } else { mismatches++; }
-      i--; j--; rd.up(); nop = 'M';
+      bool const hit = (a & c) != 0 && !(sp.n_mismatch && (a == 15 || c == 15));
+      matches += hit ? 1 : 0;
+      mismatches += hit ? 0 : 1;
     }
+    char const nop = is_i ? 'I' : (is_d ? 'D' : 'M');
+    if (!is_i) { i--; rd.up(); }
+    if (!is_d) { j--; }
     if (first_run_open) {
       if (last_run == 0 || nop == last_run_op) { last_run_op = nop; last_run++; }
       else { first_run_open = false; }
