@@ -157,6 +157,37 @@ def test_multi_shard_database_vs_oracle(ctx):
     od.close(); ix.close(); db.close(); qs.close()
 
 
+def test_ranker_ties_and_thresholds_vs_oracle(ctx):
+    """the ranker's running threshold: thousands of targets tied on the k-mer count (more than its key
+    buffer holds), few candidates (< tophits), tophits from 1 to 1024, in one and in several shards"""
+    rng = np.random.default_rng(53)
+    root = synth.random_seqs(rng, 1, 150)[0]
+    seqs = []
+    for i in range(6000):                      # 6000 near-copies: same k-mer count for thousands of them
+        s = root.copy()
+        if i % 3 == 1:
+            s[int(rng.integers(0, 150))] = synth.ACGT[int(rng.integers(0, 4))]
+        seqs.append(s[: 150 - (i % 5)].tobytes())          # length decides among equal counts, then seqno
+    other = synth.random_seqs(rng, 34000, 90)
+    seqs += [other[i].tobytes() for i in range(34000)]   # second shard: unrelated
+    seqs += [synth.mutate(rng, root, 0.1).tobytes() for _ in range(50)]
+    dbs = synth.SeqSet(seqs)
+    queries = [root.tobytes(), synth.mutate(rng, root, 0.04).tobytes(), root[:60].tobytes(),
+               other[5].tobytes(), synth.random_seqs(rng, 1, 120)[0].tobytes()]
+    qss = synth.SeqSet(queries)
+    db = ctx.seqset(dbs); qs = ctx.seqset(qss)
+    ix = ctx.index(db, 8, 0)
+    od = checkers.OracleDb(dbs)
+    for maxaccepts, maxrejects in ((1, 0), (1, 32), (8, 100), (500, 516)):
+        opts = checkers.search_opts(len(seqs), id=0.9, maxaccepts=maxaccepts, maxrejects=maxrejects)
+        seqno, count, nc = ctx.rank(ix, qs, 0, len(queries), opts.minwordmatches, opts.tophits)
+        for i, q in enumerate(queries):
+            s_, c_ = od.topscores(q, opts)
+            assert nc[i] == len(s_), (opts.tophits, i, nc[i], len(s_))
+            assert seqno[i, :nc[i]].tolist() == s_.tolist() and count[i, :nc[i]].tolist() == c_.tolist(), (opts.tophits, i)
+    od.close(); ix.close(); db.close(); qs.close()
+
+
 @pytest.mark.skipif(checkers.ref() is None, reason="oracle/_ref/libvsref.so not present")
 def test_search_vs_compiled_reference(ctx):
     """config-2 shape in miniature: 250-nt windows of a random 1500-nt database, 5 % mutated"""

@@ -290,48 +290,56 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
           uint32_t const nb = (li + NWARPS < np2) ? (llen[li + NWARPS] >> 3) : 0u;
           return na > nb ? na : nb;
         };
-        auto load_set = [&](int li, uint32_t base, uint4 (&x)[6]) {
+        // One register buffer of six vectors (three per list): as soon as a vector has been turned into
+        // counter updates its slot is refilled from the NEXT (list pair, offset), so six loads per lane
+        // stay in flight without a second buffer (48 data registers would not leave room in the 64
+        // this kernel may use at two 512-thread CTAs per SM).
+        struct ListPair { uint32_t na, nb; const uint4 * pa; const uint4 * pb; };
+        auto bounds_of = [&](int li) -> ListPair {
           int const l2 = li + NWARPS;
-          uint32_t const na = llen[li] >> 3;
-          uint32_t const nb = (l2 < np2) ? (llen[l2] >> 3) : 0u;
-          const uint4 * __restrict__ pa = reinterpret_cast<const uint4 *>(S.post + lbeg[li]);
-          const uint4 * __restrict__ pb = reinterpret_cast<const uint4 *>(S.post + (l2 < np2 ? lbeg[l2] : 0u));
-#pragma unroll
-          for (int u = 0; u < 3; u++) {
-            uint32_t const e = base + lane + 32u * u;
-            x[u] = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);
-            x[3 + u] = x[u];
-            if (e < na) { x[u] = __ldg(pa + e); }
-            if (e < nb) { x[3 + u] = __ldg(pb + e); }
-          }
+          ListPair lp;
+          lp.na = llen[li] >> 3;
+          lp.nb = (l2 < np2) ? (llen[l2] >> 3) : 0u;
+          lp.pa = reinterpret_cast<const uint4 *>(S.post + lbeg[li]);
+          lp.pb = reinterpret_cast<const uint4 *>(S.post + (l2 < np2 ? lbeg[l2] : 0u));
+          return lp;
         };
-        // software pipeline: the loads of the next (list pair, offset) are in flight while the
-        // counters of the current one are updated
         int li = warp;
         uint32_t base = 0;
         bool have = li < np2;
         uint4 cur[6];
-        if (have) { load_set(li, base, cur); }
+        uint32_t valid = 0;
+        if (have) {
+          ListPair const lp = bounds_of(li);
+#pragma unroll
+          for (int u = 0; u < 6; u++) {
+            uint32_t const e = lane + 32u * (u % 3);
+            if (e < (u < 3 ? lp.na : lp.nb)) { cur[u] = __ldg((u < 3 ? lp.pa : lp.pb) + e); valid |= 1u << u; }
+          }
+        }
         while (have) {
           int nli = li;
           uint32_t nbase = base + 96;
           if (nbase >= pair_len(li)) { nli = li + 2 * NWARPS; nbase = 0; }
           bool const nhave = nli < np2;
-          uint4 nxt[6];
-          if (nhave) { load_set(nli, nbase, nxt); }
+          ListPair lp{0u, 0u, nullptr, nullptr};
+          if (nhave) { lp = bounds_of(nli); }
+          uint32_t nvalid = 0;
 #pragma unroll
           for (int u = 0; u < 6; u++) {
-            uint32_t const w[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
-            if (w[0] == 0x80008000u) { continue; }  // padding only (real entries come first)
+            if ((valid & (1u << u)) != 0u) {
+              uint32_t const w[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-              uint32_t const a = w[k] & 0xffffu, b = w[k] >> 16;
-              atomicAdd(&counters[a >> 1], (a & 1) ? 0x10000u : 1u);
-              atomicAdd(&counters[b >> 1], (b & 1) ? 0x10000u : 1u);
+              for (int k = 0; k < 4; k++) {
+                uint32_t const a = w[k] & 0xffffu, b = w[k] >> 16;
+                atomicAdd(&counters[a >> 1], (a & 1) ? 0x10000u : 1u);
+                atomicAdd(&counters[b >> 1], (b & 1) ? 0x10000u : 1u);
+              }
             }
+            uint32_t const e = nbase + lane + 32u * (u % 3);
+            if (e < (u < 3 ? lp.na : lp.nb)) { cur[u] = __ldg((u < 3 ? lp.pa : lp.pb) + e); nvalid |= 1u << u; }
           }
-#pragma unroll
-          for (int u = 0; u < 6; u++) { cur[u] = nxt[u]; }
+          valid = nvalid;
           li = nli; base = nbase; have = nhave;
         }
       }
