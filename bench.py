@@ -99,7 +99,7 @@ def reference_arm(args, rank):
     from vsearch_b200 import synth
     cores = os.cpu_count() or 1
     if checkers.ref() is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvsref.so not built"}))
+        emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvsref.so not built"}))
         return
     lib = checkers.ref()
     dbm = synth.config2_db(N_DB, DB_LEN, SEED)
@@ -136,7 +136,7 @@ def reference_arm(args, rank):
                              "sample": f"{sample} queries per step of the same stream, reference search_batch "
                                        f"--threads {cores}"},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def allpairs_workload(args, rank, world, local):
@@ -158,7 +158,7 @@ def allpairs_workload(args, rank, world, local):
         import checkers
         cores = os.cpu_count() or 1
         if checkers.ref() is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvsref.so not built"}))
+            emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvsref.so not built"}))
             return
         lib = checkers.ref(); lib.vsref_allpairs_rows.restype = C.c_longlong
         if args.ref_rows <= 0:
@@ -177,7 +177,7 @@ def allpairs_workload(args, rank, world, local):
         r.close()
         g = tot_c / tot_t / 1e9
         cfg["rows_per_step"] = args.ref_rows
-        print(json.dumps({"impl": "reference", "metric": "allpairs_global_gcups", "value": g, "unit": "GCUPS",
+        emit(json.dumps({"impl": "reference", "metric": "allpairs_global_gcups", "value": g, "unit": "GCUPS",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "int16", "data": "synthetic", "config": cfg,
@@ -233,7 +233,7 @@ def allpairs_workload(args, rank, world, local):
         g = work[1] / (ms * 1e-3) / 1e9
         peak_ops = ctx.int_peak()
         cfg.update({"rows_per_step_per_gpu": args.rows, "parallelism": f"query rows sharded x{world}, reads NCCL-broadcast"})
-        print(json.dumps({"metric": "allpairs_global_gcups", "value": g, "unit": "GCUPS", "n_gpus": world,
+        emit(json.dumps({"metric": "allpairs_global_gcups", "value": g, "unit": "GCUPS", "n_gpus": world,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
                           "data": "synthetic", "config": cfg, "pairs_per_s": float(work[0]) / (ms * 1e-3),
@@ -251,7 +251,26 @@ def allpairs_workload(args, rank, world, local):
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(text):
+    """the result line: the only thing this program writes to its original stdout"""
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (text + "\n").encode())
+
+
+def quiet_stdout():
+    """Libraries print banners to stdout (NCCL's version line under torchrun): keep the real stdout
+    for the one JSON line and point fd 1 at stderr for everything else."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -496,7 +515,7 @@ def main():
                               "pairs_aligned_fraction": float(work_lazy[2]) / max(1.0, float(work_lazy[0]))}}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line))
+        emit(json.dumps(line))
     ix.close(); db.close(); ctx.close()
     if world > 1:
         dist.destroy_process_group()
