@@ -64,9 +64,14 @@ int vsg_ctx_sync(vsg_ctx * ctx);
  *      commands/allpairs_global.cpp:447-473).  That routine stays on the host side of the boundary:
  *      the embedding application registers it here and vsg_search_batch / vsg_allpairs call it for
  *      exactly those pairs.  query/target are indices into the sequence sets of the call, strand is
- *      1 when the query is to be reverse-complemented.  out[9] = {nwscore, alignment length,
- *      matches, mismatches, gaps, trim_q_left, trim_t_left, trim_q_right, trim_t_right} (trims as in
- *      vsg_align_pairs).  Return 0 on success.  Called from the library's worker threads, possibly
+ *      1 when the query is to be reverse-complemented.  out[10] = {nwscore, alignment length,
+ *      matches, mismatches, gaps, trim_q_left, trim_t_left, trim_q_right, trim_t_right, forbidden}
+ *      (trims as in vsg_align_pairs).  `forbidden` (preset to 0) is the application's verdict of
+ *      alignment_uses_forbidden_gap (core/searchcore.cpp:612-660): non-zero iff the alignment uses a
+ *      gap class whose penalty was given as '*'; such a hit is rejected exactly as
+ *      search_acceptable_aligned does (:677-680).  '*' penalties reach the library as values that do
+ *      not fit a 16-bit cell, which defers every pair to this callback (align_simd.cpp:1463-1479).
+ *      Return 0 on success.  Called from the library's worker threads, possibly
  *      concurrently.  Without a callback such a pair makes the call fail with VSG_EINVAL. ---- */
 typedef int (*vsg_fallback_fn)(void * user, int64_t query, int32_t strand, int64_t target, int64_t * out);
 int vsg_ctx_set_fallback(vsg_ctx * ctx, vsg_fallback_fn fn, void * user);
@@ -187,6 +192,24 @@ typedef struct vsg_search_opts {
   int64_t maxdiffs;       /* --maxdiffs (INT_MAX)          */
   int32_t leftjust;       /* --leftjust                    */
   int32_t rightjust;      /* --rightjust                   */
+  /* the remaining pre-alignment filters of search_acceptable_unaligned (core/searchcore.cpp:561-608);
+     vsg_search_batch only (vsg_allpairs ignores them, as allpairs_global's defaults do) */
+  int64_t maxqsize;       /* --maxqsize (INT64_MAX): query abundance <= maxqsize           */
+  int64_t mintsize;       /* --mintsize (0):         target abundance >= mintsize          */
+  double minsizeratio;    /* --minsizeratio (0.0):   query abundance >= ratio * target's   */
+  double maxsizeratio;    /* --maxsizeratio (DBL_MAX)                                      */
+  int32_t idprefix;       /* --idprefix (0): first n nucleotides identical (compared on the device) */
+  int32_t idsuffix;       /* --idsuffix (0): last n nucleotides identical                   */
+  int32_t self;           /* --self:   reject a target whose label equals the query's      */
+  int32_t selfid;         /* --selfid: reject a target whose sequence equals the query's   */
+  int32_t qmask_dust;     /* --qmask dust with --strand both: the caller has DUST-masked `queries`
+                             (vsg_seqset_dust); the reverse complements made inside the call are masked
+                             on their own, as search_batch_worker_fn does per strand (core/search.cpp:437-449) */
+  int32_t reserved0;
+  const int64_t * query_sizes;   /* abundance of query q0+i at [i]; NULL = 1 everywhere (db.getabundance / qsize) */
+  const int64_t * target_sizes;  /* abundance of target t at [t];   NULL = 1 everywhere                     */
+  const int64_t * query_labels;  /* --self: label identities, [i] for query q0+i resp. [t] for target t; two  */
+  const int64_t * target_labels; /*         sequences carry the same header iff their identities are equal  */
 } vsg_search_opts;
 
 typedef struct vsg_search_result {

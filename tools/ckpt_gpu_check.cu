@@ -108,19 +108,29 @@ int main(int argc, char ** argv)
   DevSeqs qs{d_qsym, d_qoff, d_qlen, ntasks}, ts{d_tsym, d_toff, d_tlen, 2 * ntasks};
 
   size_t const dyn = fast_dyn_smem(R, false);
-  CK(cudaFuncSetAttribute(nw_ckpt_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+  CK(cudaFuncSetAttribute(nw_ckpt_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+  CK(cudaFuncSetAttribute(nw_ckpt_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
   cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
   float fwd_ms = 0, tb_ms = 0;
+  // PLAIN variant: the same alignment problem under the shifted scoring S - 2, ge + 1 (every cell of anti-diagonal
+  // i+j is lowered by i+j+2: identical direction bits, all scores <= 0, every add a plain 32-bit subtract)
+  ScoreParams sp2 = sp;
+  for (int i = 0; i < 16; i++) { for (int j = 0; j < 16; j++) { sp2.S[i][j] = static_cast<int16_t>(sp.S[i][j] - 2); } }
+  for (int k = 0; k < 6; k++) { sp2.ge[k] = static_cast<int16_t>(sp.ge[k] + 1); }
+  int bad_total = 0;
+  for (int variant = 0; variant < 2; variant++) {
+  ScoreParams const & spv = variant ? sp2 : sp;
   for (int rep = 0; rep < 3; rep++) {
     cudaEventRecord(e0);
-    nw_ckpt_kernel<R><<<(ntasks + FAST_WARPS - 1) / FAST_WARPS, FAST_WARPS * 32, dyn>>>(sp, qs, ts, d_tasks, ntasks, d_row, d_col, d_stats);
+    if (variant) { nw_ckpt_kernel<R, true><<<(ntasks + FAST_WARPS - 1) / FAST_WARPS, FAST_WARPS * 32, dyn>>>(spv, qs, ts, d_tasks, ntasks, d_row, d_col, d_stats); }
+    else { nw_ckpt_kernel<R, false><<<(ntasks + FAST_WARPS - 1) / FAST_WARPS, FAST_WARPS * 32, dyn>>>(spv, qs, ts, d_tasks, ntasks, d_row, d_col, d_stats); }
     cudaEventRecord(e1);
-    tb_ckpt_kernel<<<(2 * ntasks + 127) / 128, 128>>>(sp, qs, ts, d_tasks, ntasks, R, d_row, d_col, d_stats);
+    tb_ckpt_kernel<<<(2 * ntasks + 127) / 128, 128>>>(spv, qs, ts, d_tasks, ntasks, R, d_row, d_col, d_stats);
     cudaEventRecord(e2);
     CK(cudaEventSynchronize(e2));
     cudaEventElapsedTime(&fwd_ms, e0, e1); cudaEventElapsedTime(&tb_ms, e1, e2);
     double const cells = static_cast<double>(ntasks) * 2 * Q * D;
-    std::printf("rep %d: forward %.2f ms (%.0f GCUPS), traceback %.2f ms\n", rep, fwd_ms, cells / fwd_ms / 1e6, tb_ms);
+    std::printf("variant %s rep %d: forward %.2f ms (%.0f GCUPS), traceback %.2f ms\n", variant ? "plain-sub/shifted" : "all-dpx", rep, fwd_ms, cells / fwd_ms / 1e6, tb_ms);
   }
   CK(cudaGetLastError());
 
@@ -133,10 +143,13 @@ int main(int argc, char ** argv)
     int16_t os; uint16_t oa, om, omi, og; std::vector<char> cig(Q + D + 64);
     oracle_nw16(&sc, qa.data() + static_cast<size_t>(p / 2) * Q, Q, ta.data() + static_cast<size_t>(p) * D, D, &os, &oa, &om, &omi, &og, cig.data(), cig.size());
     int32_t const * st = stats.data() + static_cast<size_t>(p) * VSG_STAT_WORDS;
-    if (st[VSG_STAT_SCORE] != os || st[VSG_STAT_ALIGNED] != oa || st[VSG_STAT_MATCHES] != om || st[VSG_STAT_MISMATCHES] != omi || st[VSG_STAT_GAPS] != og) {
-      if (++bad <= 5) { std::printf("MISMATCH pair %d: score %d/%d aligned %d/%d matches %d/%d gaps %d/%d\n", p, st[VSG_STAT_SCORE], os, st[VSG_STAT_ALIGNED], oa, st[VSG_STAT_MATCHES], om, st[VSG_STAT_GAPS], og); }
+    int const got_score = st[VSG_STAT_SCORE] + (variant ? Q + D : 0);
+    if (got_score != os || st[VSG_STAT_ALIGNED] != oa || st[VSG_STAT_MATCHES] != om || st[VSG_STAT_MISMATCHES] != omi || st[VSG_STAT_GAPS] != og) {
+      if (++bad <= 5) { std::printf("MISMATCH pair %d: score %d/%d aligned %d/%d matches %d/%d gaps %d/%d\n", p, got_score, os, st[VSG_STAT_ALIGNED], oa, st[VSG_STAT_MATCHES], om, st[VSG_STAT_GAPS], og); }
     }
   }
   std::printf("%d of %d sampled pairs differ from the oracle\n", bad, nsample);
-  return bad != 0;
+  bad_total += bad;
+  }
+  return bad_total != 0;
 }

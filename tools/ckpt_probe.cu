@@ -4,6 +4,6 @@
 void ckpt_probe_launch(const vsg::ScoreParams & sp, vsg::DevSeqs q, vsg::DevSeqs t, const vsg::FastTask * tasks, int n,
                        uint2 * rowck, uint2 * colck, int32_t * stats)
 {
-  vsg::nw_ckpt_kernel<8><<<(n + vsg::FAST_WARPS - 1) / vsg::FAST_WARPS, vsg::FAST_WARPS * 32, vsg::fast_dyn_smem(8, false)>>>(
+  vsg::nw_ckpt_kernel<8, true><<<(n + vsg::FAST_WARPS - 1) / vsg::FAST_WARPS, vsg::FAST_WARPS * 32, vsg::fast_dyn_smem(8, false)>>>(
       sp, q, t, tasks, n, rowck, colck, stats);
 }

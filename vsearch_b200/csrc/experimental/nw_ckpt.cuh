@@ -19,7 +19,7 @@ namespace vsg {
 
 constexpr int CKPT_KC = 32;   // columns between column checkpoints
 
-template <int R>
+template <int R, bool PLAIN>
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 nw_ckpt_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
                const FastTask * __restrict__ tasks, int ntasks,
@@ -71,7 +71,7 @@ nw_ckpt_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
     int const i = row0 + r;
     bool const last = (i == Q - 1);
     nQRq[r] = pk1(-(last ? QRqr : QRqi));
-    nRq[r] = pk1(-(last ? Rqr : Rqi));
+    nRq[r] = PLAIN ? pk1(last ? Rqr : Rqi) : pk1(-(last ? Rqr : Rqi));   // PLAIN: positive, subtracted with a 32-bit SUB
     Hl[r] = BIAS2 - pk1(gotl + (i + 1) * getl);
     E[r] = __vadd2(Hl[r], nQRq[r]);
     asm volatile("" : "+r"(nQRq[r]), "+r"(nRq[r]));
@@ -88,10 +88,11 @@ nw_ckpt_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
 #pragma unroll
       for (int r4 = 0; r4 < RQ; r4++) {
         uint4 v;
-        v.x = pk2(sp.S[dlo][code[4 * r4 + 0]], sp.S[dhi][code[4 * r4 + 0]]);
-        v.y = pk2(sp.S[dlo][code[4 * r4 + 1]], sp.S[dhi][code[4 * r4 + 1]]);
-        v.z = pk2(sp.S[dlo][code[4 * r4 + 2]], sp.S[dhi][code[4 * r4 + 2]]);
-        v.w = pk2(sp.S[dlo][code[4 * r4 + 3]], sp.S[dhi][code[4 * r4 + 3]]);
+        int const sg = PLAIN ? -1 : 1;   // PLAIN: scores are <= 0 (shifted scoring), stored negated and SUBtracted
+        v.x = pk2(sg * sp.S[dlo][code[4 * r4 + 0]], sg * sp.S[dhi][code[4 * r4 + 0]]);
+        v.y = pk2(sg * sp.S[dlo][code[4 * r4 + 1]], sg * sp.S[dhi][code[4 * r4 + 1]]);
+        v.z = pk2(sg * sp.S[dlo][code[4 * r4 + 2]], sg * sp.S[dhi][code[4 * r4 + 2]]);
+        v.w = pk2(sg * sp.S[dlo][code[4 * r4 + 3]], sg * sp.S[dhi][code[4 * r4 + 3]]);
         myprof[(tp * RQ + r4) * 32] = v;
       }
     }
@@ -118,7 +119,7 @@ nw_ckpt_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           int const r = 4 * r4 + u;
-          if (r < R) { t[r] = __vadd2(r == 0 ? diag_in : Hl[r - 1], Sv[u]); }
+          if (r < R) { t[r] = PLAIN ? ((r == 0 ? diag_in : Hl[r - 1]) - Sv[u]) : __vadd2(r == 0 ? diag_in : Hl[r - 1], Sv[u]); }
         }
       }
       uint32_t F = fin;
@@ -126,8 +127,8 @@ nw_ckpt_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
       for (int r = 0; r < R; r++) {
         uint32_t const h = __vimax3_u16x2(t[r], F, E[r]);
         Hl[r] = h;
-        F = __viaddmax_u16x2(h, rec.y, __vadd2(F, rec.z));
-        E[r] = __viaddmax_u16x2(h, nQRq[r], __vadd2(E[r], nRq[r]));
+        F = __viaddmax_u16x2(h, rec.y, PLAIN ? (F - rec.z) : __vadd2(F, rec.z));
+        E[r] = __viaddmax_u16x2(h, nQRq[r], PLAIN ? (E[r] - nRq[r]) : __vadd2(E[r], nRq[r]));
       }
       Hout = Hl[R - 1];
       Fout = F;
@@ -158,7 +159,7 @@ nw_ckpt_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
       uint4 rec;
       rec.x = static_cast<uint32_t>(code_to_2bit(a) + 4 * code_to_2bit(b)) * (RQ * 512u);
       rec.y = pk2(-(cc >= Dlo - 1 ? QRtr : QRti), -(cc >= Dhi - 1 ? QRtr : QRti));
-      rec.z = pk2(-(cc >= Dlo - 1 ? Rtr : Rti), -(cc >= Dhi - 1 ? Rtr : Rti));
+      rec.z = PLAIN ? pk2(cc >= Dlo - 1 ? Rtr : Rti, cc >= Dhi - 1 ? Rtr : Rti) : pk2(-(cc >= Dlo - 1 ? Rtr : Rti), -(cc >= Dhi - 1 ? Rtr : Rti));
       rec.w = BIAS2 - pk1(goql + (cc + 1) * geql);
       uint32_t const fin0 = __vadd2(rec.w, rec.y);
       int const slot = cc & (RING - 1);

@@ -15,6 +15,8 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <climits>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -43,6 +45,7 @@ struct Hit {  // the fields of struct hit (searchcore.hpp:78-126) this path need
   int target, strand;
   unsigned count;
   bool accepted, rejected, aligned, weak;
+  bool forbidden_gap;  // fallback callback's alignment_uses_forbidden_gap verdict (searchcore.cpp:612-660)
   int nwscore, nwdiff, nwgaps, nwindels, nwalignmentlength;
   int matches, mismatches;
   int internal_alignmentlength, internal_gaps, internal_indels;
@@ -55,6 +58,7 @@ struct QState {
   int ncand = 0, next = 0;
   const uint32_t * cs = nullptr;
   const uint32_t * cc = nullptr;
+  const uint8_t * cf = nullptr;  // per-candidate device verdicts of the sequence-content filters (0 = pass)
   int hit_base = 0;  // index of this state's first Hit in the batch-wide hit array
   int hit_count = 0, accepts = 0, rejects = 0, finalized = 0, delayed = 0;
   int gpos = -1;  // lazy mode: next hit of the open group to examine (-1: no group open)
@@ -65,6 +69,7 @@ struct QState {
 
 struct SearchScratch {  // per host thread, see vsg_ctx::search_scratch
   std::vector<uint32_t> h_seqno, h_count;
+  std::vector<uint8_t> h_flags;
   std::vector<int32_t> h_n;
   std::vector<QState> st;
   Hit * hits = nullptr;
@@ -103,16 +108,70 @@ void finish_hit(Hit & h, const int32_t * trims, int iddef)
   }
 }
 
-// search_acceptable_unaligned: the length-ratio filters (searchcore.cpp:573-587); the abundance, label
-// and prefix/suffix filters of that function are not offered through this ABI (defaults pass)
-bool acceptable_unaligned(const vsg_search_opts & o, int qseqlen, int64_t dseqlen)
+// abundance_ratio_cmp (searchcore.cpp:480-537): sign of value - ratio * reference; the double product
+// below 2^53, the exact 128-bit product of the ratio's mantissa above it
+int size_ratio_sign(int64_t value, double ratio, int64_t reference)
 {
-  return (qseqlen >= o.minqt * static_cast<double>(dseqlen)) &&
+  if (reference <= 0 || ratio <= 0.0) { return value > 0 ? 1 : 0; }
+  if (!std::isfinite(ratio)) { return -1; }
+  int64_t const lim = static_cast<int64_t>(1) << 53;
+  if (value < lim && reference < lim) {
+    double const prod = ratio * static_cast<double>(reference), v = static_cast<double>(value);
+    return v < prod ? -1 : (v > prod ? 1 : 0);
+  }
+  int ex = 0;
+  int64_t const mant = static_cast<int64_t>(std::ldexp(std::frexp(ratio, &ex), 53));
+  ex -= 53;
+  unsigned __int128 lhs = static_cast<uint64_t>(value);
+  unsigned __int128 rhs = static_cast<unsigned __int128>(static_cast<uint64_t>(mant)) * static_cast<uint64_t>(reference);
+  for (; ex > 0; ex--) { if ((rhs >> 126) != 0) { return -1; } rhs <<= 1; }
+  for (; ex < 0; ex++) { if ((lhs >> 126) != 0) { return 1; } lhs <<= 1; }
+  return lhs < rhs ? -1 : (lhs > rhs ? 1 : 0);
+}
+
+// search_acceptable_unaligned (searchcore.cpp:541-609).  The sequence-content tests (idprefix, idsuffix,
+// selfid) arrive as `content`, computed on the device by prefilter_kernel below (0 = all pass).
+bool acceptable_unaligned(const vsg_search_opts & o, int qseqlen, int64_t dseqlen, int64_t qsize, int64_t tsize,
+                          bool same_label, unsigned content)
+{
+  return (qsize <= o.maxqsize) && (tsize >= o.mintsize) &&
+         (size_ratio_sign(qsize, o.minsizeratio, tsize) >= 0) &&
+         (size_ratio_sign(qsize, o.maxsizeratio, tsize) <= 0) &&
+         (qseqlen >= o.minqt * static_cast<double>(dseqlen)) &&
          (qseqlen <= o.maxqt * static_cast<double>(dseqlen)) &&
          (qseqlen < dseqlen ? qseqlen >= o.minsl * static_cast<double>(dseqlen)
                             : static_cast<double>(dseqlen) >= o.minsl * qseqlen) &&
          (qseqlen < dseqlen ? qseqlen <= o.maxsl * static_cast<double>(dseqlen)
-                            : static_cast<double>(dseqlen) <= o.maxsl * qseqlen);
+                            : static_cast<double>(dseqlen) <= o.maxsl * qseqlen) &&
+         (content == 0u) && (o.self == 0 || !same_label);
+}
+
+// idprefix / idsuffix / selfid of search_acceptable_unaligned (searchcore.cpp:588-607) for every candidate
+// of every query of a ranked batch: one warp per (query, candidate) compares 4-bit codes as seqcmp does
+// (utils/seqcmp.cpp:72-92).  flags: 1 = idprefix fails, 2 = idsuffix fails, 4 = selfid fails.
+__global__ void prefilter_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const uint32_t * __restrict__ cand,
+                                 const int32_t * __restrict__ ncand, int tophits, int idprefix, int idsuffix, int selfid,
+                                 uint8_t * __restrict__ flags)
+{
+  int64_t const w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  int const lane = threadIdx.x & 31;
+  if (w >= static_cast<int64_t>(nq) * tophits) { return; }
+  int const qi = static_cast<int>(w / tophits), j = static_cast<int>(w % tophits);
+  if (j >= ncand[qi]) { return; }
+  uint32_t const t = cand[w];
+  const uint8_t * __restrict__ q = qs.sym + qs.off[q0 + qi];
+  const uint8_t * __restrict__ d = db.sym + db.off[t];
+  int const ql = qs.len[q0 + qi], dl = db.len[t];
+  auto differ = [&](const uint8_t * a, const uint8_t * b, int n) -> bool {
+    int bad = 0;
+    for (int i = lane; i < n; i += 32) { bad |= ((a[i] ^ b[i]) & 15) != 0; }
+    return __any_sync(0xffffffffu, bad) != 0;
+  };
+  unsigned f = 0;
+  if (idprefix > 0 && (ql < idprefix || dl < idprefix || differ(q, d, idprefix))) { f |= 1u; }
+  if (idsuffix > 0 && (ql < idsuffix || dl < idsuffix || differ(q + ql - idsuffix, d + dl - idsuffix, idsuffix))) { f |= 2u; }
+  if (selfid != 0 && ql == dl && !differ(q, d, ql)) { f |= 4u; }
+  if (lane == 0) { flags[w] = static_cast<uint8_t>(f); }
 }
 
 // search_acceptable_aligned (searchcore.cpp:664-737)
@@ -120,6 +179,7 @@ bool acceptable_aligned(Hit & h, double opt_id, double opt_weak_id, const vsg_se
 {
   double const mid = 100.0 * h.matches / (h.matches + h.mismatches);  // 0/0 -> NaN fails the test, as in the reference
   if (h.id >= 100.0 * opt_weak_id && h.mismatches <= o.maxsubs && h.internal_gaps <= o.maxgaps &&
+      !h.forbidden_gap &&  // '*' gap penalties, searchcore.cpp:677-680
       h.internal_alignmentlength >= o.mincols &&
       (o.leftjust == 0 || h.trim_q_left + h.trim_t_left == 0) &&
       (o.rightjust == 0 || h.trim_q_right + h.trim_t_right == 0) &&
@@ -153,6 +213,9 @@ extern "C" void vsg_search_opts_default(vsg_search_opts * o)
   o->maxid = 1.0; o->mid = 0.0; o->query_cov = 0.0; o->target_cov = 0.0;
   o->maxsubs = 2147483647; o->maxgaps = 2147483647; o->mincols = 0; o->maxdiffs = 2147483647;
   o->leftjust = 0; o->rightjust = 0;
+  o->maxqsize = INT64_MAX; o->mintsize = 0; o->minsizeratio = 0.0; o->maxsizeratio = 1.7976931348623157e308;
+  o->idprefix = 0; o->idsuffix = 0; o->self = 0; o->selfid = 0; o->qmask_dust = 0; o->reserved0 = 0;
+  o->query_sizes = nullptr; o->target_sizes = nullptr; o->query_labels = nullptr; o->target_labels = nullptr;
 }
 
 extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * db,
@@ -189,6 +252,11 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   if (tophits64 > 1024) { Error::set("vsg_search_batch: maxaccepts+maxrejects+8 > 1024 is not supported on the device ranker"); return VSG_EINVAL; }
   int const tophits = static_cast<int>(tophits64);
   int const nstrands = opts->strand_both ? 2 : 1;
+  if (opts->self != 0 && (opts->query_labels == nullptr || opts->target_labels == nullptr)) {
+    Error::set("vsg_search_batch: --self needs query_labels and target_labels"); return VSG_EINVAL;
+  }
+  if (opts->idprefix < 0 || opts->idsuffix < 0) { Error::set("vsg_search_batch: idprefix/idsuffix must not be negative"); return VSG_EINVAL; }
+  bool const content_filters = opts->idprefix > 0 || opts->idsuffix > 0 || opts->selfid != 0;
 
   // Sub-batches run on a few host threads, each with its own child context (stream + scratch):
   // while one thread replays accept/reject decisions or builds task lists, the kernels of the
@@ -248,11 +316,22 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
     int64_t const bn = std::min(bn_req, nq - b0);
     vsg_seqset * rc_set = nullptr;
     if (nstrands == 2) {
-      int const r = seqset_revcomp(c, queries, q0 + b0, bn, &rc_set);
+      int r = seqset_revcomp(c, queries, q0 + b0, bn, &rc_set);
       if (r != VSG_OK) { return r; }
+      // each strand is masked on its own (search.cpp:437-449); dust() upper-cases first, so the case the
+      // reverse complement inherited from the masked plus strand does not matter
+      if (opts->qmask_dust != 0 && (r = vsg_seqset_dust(c, rc_set)) != VSG_OK) { vsg_seqset_destroy(rc_set); return r; }
     }
     size_t const cells = static_cast<size_t>(bn) * tophits;
     h_seqno.resize(cells * nstrands); h_count.resize(cells * nstrands); h_n.resize(static_cast<size_t>(bn) * nstrands);
+    if (content_filters) { sc.h_flags.resize(cells * nstrands); }
+    // search_acceptable_unaligned for candidate `target` of the batch's query `ql` (searchcore.cpp:541-609)
+    auto unaligned_ok = [&](int target, int64_t ql, int sqlen, unsigned content) -> bool {
+      int64_t const qsize = opts->query_sizes != nullptr ? opts->query_sizes[b0 + ql] : 1;
+      int64_t const tsize = opts->target_sizes != nullptr ? opts->target_sizes[target] : 1;
+      bool const same_label = opts->self != 0 && opts->query_labels[b0 + ql] == opts->target_labels[target];
+      return acceptable_unaligned(*opts, sqlen, db->h_len[static_cast<size_t>(target)], qsize, tsize, same_label, content);
+    };
     for (int s = 0; s < nstrands; s++) {
       uint32_t *d_seqno, *d_count; int32_t *d_n, *d_status;
       const vsg_seqset * qset = (s == 0) ? queries : rc_set;
@@ -263,6 +342,16 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
       VSG_CUDA_OK(cudaMemcpyAsync(h_seqno.data() + cells * s, d_seqno, sizeof(uint32_t) * cells, cudaMemcpyDeviceToHost, c->stream));
       VSG_CUDA_OK(cudaMemcpyAsync(h_count.data() + cells * s, d_count, sizeof(uint32_t) * cells, cudaMemcpyDeviceToHost, c->stream));
       VSG_CUDA_OK(cudaMemcpyAsync(h_n.data() + bn * s, d_n, sizeof(int32_t) * bn, cudaMemcpyDeviceToHost, c->stream));
+      if (content_filters) {
+        if ((r = c->pre_flags.reserve(cells + 16)) != VSG_OK) { if (rc_set) { vsg_seqset_destroy(rc_set); } return r; }
+        VSG_CUDA_OK(cudaMemsetAsync(c->pre_flags.p, 0, cells, c->stream));
+        int64_t const nwarps = bn * tophits;
+        prefilter_kernel<<<static_cast<unsigned>((nwarps * 32 + 255) / 256), 256, 0, c->stream>>>(
+            qset->d, qq0, static_cast<int>(bn), db->d, d_seqno, d_n, tophits, opts->idprefix, opts->idsuffix, opts->selfid,
+            static_cast<uint8_t *>(c->pre_flags.p));
+        count_launch();
+        VSG_CUDA_OK(cudaMemcpyAsync(sc.h_flags.data() + cells * s, c->pre_flags.p, cells, cudaMemcpyDeviceToHost, c->stream));
+      }
       VSG_CUDA_OK(cudaMemcpyAsync(&status, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
       VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
       rank_collect_time(c);
@@ -291,6 +380,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
         S.ncand = h_n[static_cast<size_t>(s) * bn + q];
         S.cs = h_seqno.data() + cells * s + static_cast<size_t>(q) * tophits;
         S.cc = h_count.data() + cells * s + static_cast<size_t>(q) * tophits;
+        S.cf = content_filters ? sc.h_flags.data() + cells * s + static_cast<size_t>(q) * tophits : nullptr;
         S.hit_base = static_cast<int>((static_cast<size_t>(s) * bn + q) * tophits);
       }
     }
@@ -320,8 +410,9 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
                 Hit & h = hits[static_cast<size_t>(S.hit_base) + S.hit_count];
                 std::memset(&h, 0, sizeof(Hit));
                 h.target = static_cast<int>(S.cs[S.next]); h.count = S.cc[S.next]; h.strand = strand;
+                unsigned const content = S.cf != nullptr ? S.cf[S.next] : 0u;
                 S.next++;
-                if (acceptable_unaligned(*opts, sqlen, db->h_len[static_cast<size_t>(h.target)])) { S.delayed++; }
+                if (unaligned_ok(h.target, ql, sqlen, content)) { S.delayed++; }
                 else { h.rejected = true; }
                 S.hit_count++;
                 if (S.delayed == MAXDELAYED) { trigger = true; break; }
@@ -374,12 +465,13 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
           std::memset(&h, 0, sizeof(Hit));
           h.target = static_cast<int>(S.cs[S.next]); h.count = S.cc[S.next];
           h.strand = static_cast<int>(si / static_cast<size_t>(bn));
+          unsigned const content = S.cf != nullptr ? S.cf[S.next] : 0u;
           S.next++;
           {
             int const sstrand = static_cast<int>(si / static_cast<size_t>(bn));
             int64_t const sql = static_cast<int64_t>(si % static_cast<size_t>(bn));
             int const sqlen = (sstrand == 0 ? queries->h_len[static_cast<size_t>(q0 + b0 + sql)] : rc_set->h_len[static_cast<size_t>(sql)]);
-            if (acceptable_unaligned(*opts, sqlen, db->h_len[static_cast<size_t>(h.target)])) { S.delayed++; }
+            if (unaligned_ok(h.target, sql, sqlen, content)) { S.delayed++; }
             else { h.rejected = true; }
           }
           S.hit_count++;
@@ -519,7 +611,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
           if (S.rejects < maxrejects && S.accepts < maxaccepts) {
             Hit & h = hits[static_cast<size_t>(S.hit_base) + x];
             if (h.rejected) { S.rejects++; continue; }
-            int64_t fb[9];
+            int64_t fb[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
             bool const diverted = (a_score[i] == VSG_SCORE_SENTINEL);
             if (diverted) {
               // the reference's LinearMemoryAligner path (searchcore.cpp:806-832), host side of the boundary
@@ -541,6 +633,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
             if (diverted) {
               h.nwscore = static_cast<int>(fb[0]); nal = fb[1]; nma = fb[2]; nmi = fb[3]; nga = fb[4];
               for (int z = 0; z < 4; z++) { trims4[z] = static_cast<int32_t>(fb[5 + z]); }
+              h.forbidden_gap = fb[9] != 0;
             }
             h.nwalignmentlength = static_cast<int>(nal);
             h.nwdiff = static_cast<int>(nal - nma);
@@ -720,7 +813,7 @@ extern "C" int vsg_allpairs(vsg_ctx * c, const vsg_seqset * set, int64_t row0, i
       int64_t tl = 0;
       for (int64_t j = i + 1; j < n; j++) {
         int const dl = set->h_len[static_cast<size_t>(j)];
-        if (!acceptable_unaligned(*opts, ql, dl)) { continue; }  // allpairs_global.cpp:407-414
+        if (!acceptable_unaligned(*opts, ql, dl, 1, 1, false, 0u)) { continue; }  // allpairs_global.cpp:407-414 (defaults for the rest)
         pq.push_back(static_cast<uint32_t>(i)); pt.push_back(static_cast<uint32_t>(j)); tl += dl;
       }
       cells += static_cast<int64_t>(ql) * tl;
@@ -742,7 +835,7 @@ extern "C" int vsg_allpairs(vsg_ctx * c, const vsg_seqset * set, int64_t row0, i
       int const qlen = set->h_len[static_cast<size_t>(i)];
       for (; k < np && pq[static_cast<size_t>(k)] == i; k++) {
         int64_t const j = pt[static_cast<size_t>(k)];
-        int64_t fb[9];
+        int64_t fb[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         bool const diverted = (sc[static_cast<size_t>(k)] == VSG_SCORE_SENTINEL);
         if (diverted && (c->fallback == nullptr || c->fallback(c->fallback_user, i, 0, j, fb) != 0)) {
           Error::set("vsg_allpairs: a pair was deferred to the linear-memory aligner (core/linmemalign.cpp) "
@@ -760,6 +853,7 @@ extern "C" int vsg_allpairs(vsg_ctx * c, const vsg_seqset * set, int64_t row0, i
         if (diverted) {
           h.nwscore = static_cast<int>(fb[0]); nal = fb[1]; nma = fb[2]; nmi = fb[3]; nga = fb[4];
           for (int z = 0; z < 4; z++) { trims4[z] = static_cast<int32_t>(fb[5 + z]); }
+          h.forbidden_gap = fb[9] != 0;
         }
         h.nwalignmentlength = static_cast<int>(nal);
         h.nwdiff = static_cast<int>(nal - nma);

@@ -39,7 +39,12 @@ class SearchOpts(C.Structure):
                 ("minqt", C.c_double), ("maxqt", C.c_double), ("minsl", C.c_double), ("maxsl", C.c_double),
                 ("maxid", C.c_double), ("mid", C.c_double), ("query_cov", C.c_double), ("target_cov", C.c_double),
                 ("maxsubs", C.c_int64), ("maxgaps", C.c_int64), ("mincols", C.c_int64), ("maxdiffs", C.c_int64),
-                ("leftjust", C.c_int32), ("rightjust", C.c_int32)]
+                ("leftjust", C.c_int32), ("rightjust", C.c_int32),
+                ("maxqsize", C.c_int64), ("mintsize", C.c_int64), ("minsizeratio", C.c_double),
+                ("maxsizeratio", C.c_double), ("idprefix", C.c_int32), ("idsuffix", C.c_int32),
+                ("self", C.c_int32), ("selfid", C.c_int32), ("qmask_dust", C.c_int32), ("reserved0", C.c_int32),
+                ("query_sizes", C.POINTER(C.c_int64)), ("target_sizes", C.POINTER(C.c_int64)),
+                ("query_labels", C.POINTER(C.c_int64)), ("target_labels", C.POINTER(C.c_int64))]
 
 
 class Profile(C.Structure):
@@ -169,14 +174,14 @@ class Context:
             self.h = None
 
     def set_fallback(self, fn):
-        """fn(query_index, strand, target_index) -> 9 ints (score, alnlen, matches, mismatches, gaps,
-        trim_q_left, trim_t_left, trim_q_right, trim_t_right); see vsg_ctx_set_fallback."""
+        """fn(query_index, strand, target_index) -> 9 or 10 ints (score, alnlen, matches, mismatches, gaps,
+        trim_q_left, trim_t_left, trim_q_right, trim_t_right[, forbidden]); see vsg_ctx_set_fallback."""
         proto = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.POINTER(C.c_int64))
 
         def tramp(_user, q, strand, t, out):
             try:
                 vals = fn(int(q), int(strand), int(t))
-                for i in range(9):
+                for i in range(len(vals)):
                     out[i] = int(vals[i])
                 return 0
             except Exception:
