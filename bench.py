@@ -37,6 +37,65 @@ sys.path.insert(0, ROOT)
 
 N_DB, DB_LEN, Q_LEN, DIV, SEED = 100_000, 1500, 250, 0.05, 2024
 IDENT, MAXACC, MAXREJ, K = 0.9, 1, 32, 8
+WORKLOADS = {
+    # configs[1]: the headline
+    "usearch": dict(n_db=100_000, db_len=1500, q_len=250, div=0.05, seed=2024, ident=0.9,
+                    name="usearch_global 250nt queries vs 100k x 1500nt DB, id 0.9 (configs[1])"),
+    # configs[3] shape: 31 index shards, 2.4 GB of postings
+    "c4": dict(n_db=1_000_000, db_len=1200, q_len=150, div=0.10, seed=4, ident=0.85,
+               name="usearch_global 150nt queries vs 1M x 1200nt DB, id 0.85 (configs[3] shape)"),
+}
+
+
+def set_workload(name):
+    global N_DB, DB_LEN, Q_LEN, DIV, SEED, IDENT, WL_NAME
+    w = WORKLOADS[name]
+    N_DB, DB_LEN, Q_LEN, DIV, SEED, IDENT = w["n_db"], w["db_len"], w["q_len"], w["div"], w["seed"], w["ident"]
+    WL_NAME = w["name"]
+
+
+WL_NAME = WORKLOADS["usearch"]["name"]
+
+
+def host_info():
+    """what the CPU arm ran on: the same "128 cores" gave 9.5 and 69 GCUPS on two boxes of the pool in round 1"""
+    model = ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    try:
+        la = [round(x, 2) for x in os.getloadavg()]
+    except Exception:
+        la = None
+    return {"nproc": os.cpu_count(), "cpu_model": model, "loadavg_1_5_15": la}
+
+
+def gpu_first_targets(qs, dust=False):
+    """first hit per query through the product path (C ABI), for the parity gate; None without a GPU"""
+    try:
+        from vsearch_b200 import lib as vlib, synth
+        ctx = vlib.Context(int(os.environ.get("LOCAL_RANK", "0")))
+    except Exception:
+        return None
+    from vsearch_b200 import synth
+    dbm = synth.config2_db(N_DB, DB_LEN, SEED)
+    db = ctx.seqset(synth.SeqSet.from_matrix(dbm))
+    if dust:
+        db.dust()
+    ix = ctx.index(db, K, 1 if dust else 0)
+    h = ctx.seqset(qs)
+    if dust:
+        h.dust()
+    o = vlib.default_search_opts()
+    o.id = IDENT; o.maxaccepts = MAXACC; o.maxrejects = MAXREJ; o.wordlength = K; o.mask_lower = 1 if dust else 0
+    res, counts, _ = ctx.search(ix, db, h, 0, len(qs), o, 1)
+    out = np.array([res[i].target if counts[i] > 0 else -1 for i in range(len(qs))], dtype=np.int32)
+    h.close(); ix.close(); db.close(); ctx.close()
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -91,7 +150,8 @@ def pinned_seqset(ss):
 
 
 def reference_arm(args, rank):
-    """Times the unmodified reference on this box's host cores (rank 0 only)."""
+    """Times the unmodified reference on this box's host cores (rank 0 only).  Outside the timed region the
+    same queries also go through the product path (if a GPU is present) and the first hit per query must agree."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -102,13 +162,15 @@ def reference_arm(args, rank):
         emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvsref.so not built"}))
         return
     lib = checkers.ref()
+    dust = 1 if args.masking == "dust" else 0
     dbm = synth.config2_db(N_DB, DB_LEN, SEED)
     dbs = synth.SeqSet.from_matrix(dbm)
     t0 = time.time()
-    r = checkers.RefDb(dbs, k=K, id=IDENT, maxaccepts=MAXACC, maxrejects=MAXREJ, dust=0)
+    r = checkers.RefDb(dbs, k=K, id=IDENT, maxaccepts=MAXACC, maxrejects=MAXREJ, dust=dust)
     build_s = time.time() - t0
     sample = args.ref_sample
     times, cells_l, pairs_l = [], [], []
+    last_qs, last_ft = None, None
     for step in range(args.warmup + args.steps):
         qs, _ = synth.config2_query_batch(dbm, sample, Q_LEN, DIV, SEED, batch=step)
         ft = np.zeros(sample, dtype=np.int32)
@@ -122,21 +184,32 @@ def reference_arm(args, rank):
         lib.vsref_work_get(C.byref(p), C.byref(c), C.byref(k))
         if step >= args.warmup:
             times.append(dt); cells_l.append(c.value); pairs_l.append(p.value)
+        last_qs, last_ft = qs, ft
     r.close()
+    # parity gate (not timed): the last step's queries through the product path
+    parity = {"parity_checked": 0, "parity_mismatches": 0}
+    got = gpu_first_targets(last_qs, dust=bool(dust)) if not args.no_parity else None
+    if got is not None:
+        parity = {"parity_checked": int(sample), "parity_mismatches": int((got != last_ft).sum())}
     tot = sum(times)
     gcups = sum(cells_l) / tot / 1e9
     line = {"impl": "reference", "metric": "usearch_global_gcups", "value": gcups, "unit": "GCUPS",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * tot / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-            "config": {"workload": "usearch_global 250nt queries vs 100k x 1500nt DB, id 0.9 (configs[1])",
-                       "queries_per_step": sample, "masking": "none", "reference_index_build_s": round(build_s, 1)},
+            "config": {"workload": WL_NAME, "queries_per_step": sample, "masking": args.masking,
+                       "wordlength": K, "maxaccepts": MAXACC, "maxrejects": MAXREJ,
+                       "reference_index_build_s": round(build_s, 1)},
             "queries_per_s": sample * args.steps / tot, "pairs_per_s": sum(pairs_l) / tot,
+            "host": host_info(),
             "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": "reference",
                              "sample": f"{sample} queries per step of the same stream, reference search_batch "
                                        f"--threads {cores}"},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line.update(parity)
     emit(json.dumps(line))
+    if parity["parity_mismatches"]:
+        raise SystemExit(3)
 
 
 def allpairs_workload(args, rank, world, local):
@@ -277,11 +350,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="vsg", choices=["vsg", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="queries per step per GPU")
-    ap.add_argument("--ref-sample", type=int, default=8192, help="queries per step of the reference arm")
+    ap.add_argument("--ref-sample", type=int, default=16384, help="queries per step of the reference arm")
+    ap.add_argument("--masking", default="none", choices=["none", "dust"],
+                    help="none (headline, as round 1) or dust = the reference's default --qmask/--dbmask, DUST on the device")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity gate against the reference")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="queries of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="usearch", choices=["usearch", "allpairs"],
-                    help="usearch = configs[1] (default, the headline); allpairs = configs[4] shape (dense N^2 DP)")
+    ap.add_argument("--workload", default="usearch", choices=["usearch", "c4", "allpairs"],
+                    help="usearch = configs[1] (default, the headline); c4 = configs[3] shape (1M x 1200 DB, 150-nt queries, "
+                         "id 0.85); allpairs = configs[4] shape (dense N^2 DP)")
     ap.add_argument("--rows", type=int, default=32, help="allpairs: query rows per step per GPU")
     ap.add_argument("--ref-rows", type=int, default=0,
                     help="allpairs: query rows per step of the reference arm (0 = one per host thread)")
@@ -296,6 +373,7 @@ def main():
     if args.workload == "allpairs":
         allpairs_workload(args, rank, world, local)
         return
+    set_workload(args.workload)
     if args.impl == "reference":
         reference_arm(args, rank)
         return
@@ -331,10 +409,17 @@ def main():
         db = ctx.seqset_from_device(d_cat.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), n)
     else:
         db = ctx.seqset(synth.SeqSet.from_matrix(dbm))
-    ix = ctx.index(db, K, 0)
+    dust = args.masking == "dust"
+    t_ix = time.perf_counter()
+    if dust:
+        db.dust()          # --dbmask dust on the device (core/mask.cpp:79-188)
+    ix = ctx.index(db, K, 1 if dust else 0)
+    ctx.sync()
+    index_build_ms = 1e3 * (time.perf_counter() - t_ix)
 
     opts = vlib.default_search_opts()
     opts.id = IDENT; opts.maxaccepts = MAXACC; opts.maxrejects = MAXREJ; opts.wordlength = K
+    opts.mask_lower = 1 if dust else 0
     max_results = 1
 
     nsteps = args.warmup + args.steps
@@ -348,12 +433,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_steps(e2e: bool, lazy: bool = False):
-        """returns (device ms for the K timed steps, work, launches, profile, clocks)"""
+    def run_steps(e2e: bool, lazy: bool = False, mask=None):
+        """returns (device ms for the K timed steps, work, launches, profile, clocks).  mask = (db, index): the
+        DUST leg — queries are masked on the device inside the timed region, database and index are the masked ones"""
         opts.lazy = 1 if lazy else 0
+        use_db, use_ix = (db, ix) if mask is None else mask
+        qdust = dust or mask is not None
+        opts.mask_lower = 1 if qdust else 0
         handles = None
         if not e2e:
             handles = [ctx.seqset(b) for b in batches]
+            if qdust:
+                for hh in handles:
+                    hh.dust()
         work_tot = np.zeros(4, dtype=np.int64)
         ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
         sampler = None
@@ -366,7 +458,9 @@ def main():
                 launches0 = vlib.launch_count()
                 ev0.record(stream)
             h = ctx.seqset(batches[step]) if e2e else handles[step]
-            res, counts, work = ctx.search(ix, db, h, 0, args.batch, opts, max_results)
+            if e2e and qdust:
+                h.dust()       # --qmask dust (commands/usearch_global.cpp:386-389), inside the timed region
+            res, counts, work = ctx.search(use_ix, use_db, h, 0, args.batch, opts, max_results)
             if e2e:
                 h.close()
             if step >= args.warmup:
@@ -397,6 +491,18 @@ def main():
     # job is the same, the DP cells actually computed are fewer, so its "GCUPS" is job-equivalent only
     ms_lazy, work_lazy, _, _, _, _ = run_steps(e2e=True, lazy=True)
     opts.lazy = 0
+    # the reference's DEFAULT masking (DUST on queries and database) as an extra leg when the headline runs unmasked
+    dust_leg = None
+    if not dust and args.workload == "usearch":
+        db2 = ctx.seqset(synth.SeqSet.from_matrix(dbm)); db2.dust()
+        ix2 = ctx.index(db2, K, 1)
+        ms_d, work_d, _, _, _, _ = run_steps(e2e=True, mask=(db2, ix2))
+        dust_leg = {"note": "--qmask dust --dbmask dust (the reference's defaults): DUST of every query batch on the device "
+                            "inside the timed e2e region, database masked before indexing",
+                    "ms_per_step": ms_d / args.steps, "e2e_gcups": float(work_d[1]) / (ms_d * 1e-3) / 1e9,
+                    "queries_per_s": args.batch * world * args.steps / (ms_d * 1e-3)}
+        ix2.close(); db2.close()
+    opts.mask_lower = 1 if dust else 0
 
     value = work_dev[1] / (ms_dev * 1e-3) / 1e9
     e2e_value = work_e2e[1] / (ms_e2e * 1e-3) / 1e9
@@ -454,6 +560,7 @@ def main():
 
     # ---- cpu_baseline: the unmodified reference on this box's cores, bounded sample ---------------
     cpu_baseline = None
+    parity = {"parity_checked": 0, "parity_mismatches": 0}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import checkers
@@ -462,7 +569,8 @@ def main():
         qs, _ = synth.config2_query_batch(dbm, sample, Q_LEN, DIV, SEED, batch=0)
         if checkers.ref() is not None:
             rlib = checkers.ref()
-            r = checkers.RefDb(synth.SeqSet.from_matrix(dbm), k=K, id=IDENT, maxaccepts=MAXACC, maxrejects=MAXREJ, dust=0)
+            r = checkers.RefDb(synth.SeqSet.from_matrix(dbm), k=K, id=IDENT, maxaccepts=MAXACC, maxrejects=MAXREJ,
+                               dust=1 if dust else 0)
             ft = np.zeros(sample, dtype=np.int32)
             rlib.vsref_work_reset()
             t0 = time.perf_counter()
@@ -475,7 +583,17 @@ def main():
             r.close()
             cpu_baseline = {"value": c.value / dt / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference",
                             "sample": f"first {sample} queries of batch 0, reference search_batch --threads {cores}, "
-                                      f"{dt:.1f} s", "queries_per_s": sample / dt}
+                                      f"{dt:.1f} s", "queries_per_s": sample / dt, "host": host_info()}
+            if not args.no_parity:
+                # PARITY GATE: the product path's first hit for the same queries must equal the reference's
+                hq = ctx.seqset(qs)
+                if dust:
+                    hq.dust()
+                opts.lazy = 0
+                resp, cntp, _ = ctx.search(ix, db, hq, 0, sample, opts, 1)
+                gotp = np.array([resp[i].target if cntp[i] > 0 else -1 for i in range(sample)], dtype=np.int32)
+                hq.close()
+                parity = {"parity_checked": int(sample), "parity_mismatches": int((gotp != ft).sum())}
         else:
             od = checkers.OracleDb(synth.SeqSet.from_matrix(dbm))
             oo = checkers.search_opts(N_DB, id=IDENT, maxaccepts=MAXACC, maxrejects=MAXREJ)
@@ -494,9 +612,10 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
                 "data": "synthetic",
-                "config": {"workload": "usearch_global 250nt queries vs 100k x 1500nt DB, id 0.9 (configs[1])",
+                "config": {"workload": WL_NAME,
                            "queries_per_step_per_gpu": args.batch, "global_queries_per_step": args.batch * world,
-                           "masking": "none", "wordlength": K, "maxaccepts": MAXACC, "maxrejects": MAXREJ,
+                           "masking": args.masking, "wordlength": K, "maxaccepts": MAXACC, "maxrejects": MAXREJ,
+                           "index_build_ms_per_gpu": round(index_build_ms, 1),
                            "parallelism": f"query-sharded x{world}, DB NCCL-broadcast",
                            "l2": "per-step working set (index 300 MB + direction blocks > 10 GB) exceeds the 126 MB L2"},
                 "queries_per_s": args.batch * world * args.steps / (ms_dev * 1e-3),
@@ -515,10 +634,15 @@ def main():
                               "pairs_aligned_fraction": float(work_lazy[2]) / max(1.0, float(work_lazy[0]))}}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
+        if dust_leg is not None:
+            line["dust_mode"] = dust_leg
+        line.update(parity)
         emit(json.dumps(line))
     ix.close(); db.close(); ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity["parity_mismatches"]:
+        raise SystemExit(3)
 
 
 if __name__ == "__main__":

@@ -290,6 +290,37 @@ int vsref_db_search_batch(void * h, int nq, const char * qcat, const int64_t * q
   return hits;
 }
 
+/* the same multi-threaded search_batch with every result record kept (results[q*max_results + j], fields
+   flattened to plain arrays as in vsref_db_search): the at-scale parity tests compare full rows. */
+void vsref_db_search_batch_rows(void * h, int nq, const char * qcat, const int64_t * qoff, const int * qlen,
+                                int threads, int max_results, int * counts,
+                                int * target, double * id, int * matches, int * mismatches, int * gaps,
+                                int * alnlen, int * accepted, int * strand)
+{
+  RefDb * r = static_cast<RefDb *>(h);
+  std::vector<std::string> seqs(static_cast<size_t>(nq)), heads(static_cast<size_t>(nq));
+  std::vector<const char *> ps(static_cast<size_t>(nq)), ph(static_cast<size_t>(nq));
+  std::vector<int64_t> sizes(static_cast<size_t>(nq), 1);
+  for (int q = 0; q < nq; q++) {
+    seqs[static_cast<size_t>(q)].assign(qcat + qoff[q], static_cast<size_t>(qlen[q]));
+    heads[static_cast<size_t>(q)] = "q" + std::to_string(q);
+    ps[static_cast<size_t>(q)] = seqs[static_cast<size_t>(q)].c_str();
+    ph[static_cast<size_t>(q)] = heads[static_cast<size_t>(q)].c_str();
+  }
+  Parameters p = r->params;
+  p.opt_threads = threads;
+  std::vector<search_result_s> res(static_cast<size_t>(nq) * static_cast<size_t>(max_results));
+  search_batch(p, r->dbindex, r->db, ps.data(), ph.data(), qlen, sizes.data(), nq, res.data(), max_results, counts);
+  for (int q = 0; q < nq; q++) {
+    for (int j = 0; j < counts[q]; j++) {
+      size_t const o = static_cast<size_t>(q) * static_cast<size_t>(max_results) + static_cast<size_t>(j);
+      search_result_s const & x = res[o];
+      target[o] = x.target; id[o] = x.id; matches[o] = x.matches; mismatches[o] = x.mismatches;
+      gaps[o] = x.gaps; alnlen[o] = x.alignment_length; accepted[o] = x.accepted ? 1 : 0; strand[o] = x.strand;
+    }
+  }
+}
+
 /* LinearMemoryAligner::align + alignstats (core/linmemalign.cpp) with the session's scoring: the
    reference's answer for pairs its 16-bit aligner defers.  out = {score, alnlen, matches,
    mismatches, gaps}; the CIGAR goes to cigar (cap bytes). */

@@ -219,6 +219,21 @@ class RefDb:
                                      _p(length, C.c_uint32))
         return seqno[:n].copy(), count[:n].copy()
 
+    def search_rows(self, qs, max_results=8, threads=None):
+        """the reference's own multi-threaded search_batch, every record kept: (counts, dict of flat arrays)"""
+        nq = len(qs)
+        threads = threads or (os.cpu_count() or 1)
+        counts = np.zeros(nq, dtype=np.int32)
+        m = nq * max_results
+        a = {k: np.zeros(m, dtype=np.int32) for k in ("target", "matches", "mismatches", "gaps", "alnlen", "accepted", "strand")}
+        a["id"] = np.zeros(m, dtype=np.float64)
+        ref().vsref_db_search_batch_rows(C.c_void_p(self.h), C.c_int(nq), _p(qs.cat, C.c_char), _p(qs.offs, C.c_int64),
+                                         _p(qs.lens, C.c_int), C.c_int(threads), C.c_int(max_results), _p(counts, C.c_int),
+                                         _p(a["target"], C.c_int), _p(a["id"], C.c_double), _p(a["matches"], C.c_int),
+                                         _p(a["mismatches"], C.c_int), _p(a["gaps"], C.c_int), _p(a["alnlen"], C.c_int),
+                                         _p(a["accepted"], C.c_int), _p(a["strand"], C.c_int))
+        return counts, a
+
     def search(self, qs, max_results=8):
         nq = len(qs)
         counts = np.zeros(nq, dtype=np.int32)

@@ -1,25 +1,27 @@
-// CPU check of vsearch_b200/csrc/experimental/tb_ckpt.h (round-2 groundwork) against the oracle.
-// A scalar model of nw_ckpt_kernel fills the checkpoint arrays in the DEVICE layout (32 lanes x R rows,
-// wavefront steps, two targets per task as biased 16-bit halves); the host/device traceback then has
-// to reproduce the oracle's score, statistics and CIGAR for both targets.
+// CPU check of vsearch_b200/csrc/tb_ckpt.h (the traceback of the checkpoint aligner) against the oracle.
+// A scalar model of nw_ckpt_kernel (align_ckpt.cuh) fills the checkpoint arrays in the DEVICE layout (32 lanes x
+// R rows, wavefront steps, chunk-aligned column checkpoints, two targets per task as biased 16-bit halves) under
+// the SHIFTED scoring the kernel runs with (S - 2c, ge + c); the host/device traceback then has to reproduce
+// the oracle's score (after undoing the shift), statistics and CIGAR for both targets.
 //   g++ -O2 -std=c++17 -I oracle tools/ckpt_host_check.cpp -Loracle -loracle -Wl,-rpath,$PWD/oracle -o /tmp/ckpt_host_check
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <random>
 #include <string>
 #include <vector>
 
 #include "oracle.h"
-#include "../vsearch_b200/csrc/experimental/tb_ckpt.h"
+#include "../vsearch_b200/csrc/tb_ckpt.h"
 
 using namespace vsg::ckpt;
 
 struct Score {
   int16_t S[16][16];
   int go[6], ge[6];
-  int n_mismatch;
+  int n_mismatch, match, mismatch, shift;
 };
 
 static bool ambiguous4(unsigned c) { return __builtin_popcount(c) != 1; }
@@ -28,6 +30,7 @@ static void build(const oracle_scoring & o, Score & p)
 {
   for (int k = 0; k < 6; k++) { p.go[k] = static_cast<int>(o.v[2 + k]); p.ge[k] = static_cast<int>(o.v[8 + k]); }
   p.n_mismatch = o.n_mismatch;
+  p.match = static_cast<int>(o.v[0]); p.mismatch = static_cast<int>(o.v[1]); p.shift = 0;
   for (unsigned i = 0; i < 16; i++) {
     for (unsigned j = 0; j < 16; j++) {
       int v;
@@ -38,6 +41,20 @@ static void build(const oracle_scoring & o, Score & p)
       p.S[i][j] = static_cast<int16_t>(v);
     }
   }
+}
+
+// the shifted scoring of align_ckpt.cuh (vsg_api.cu: shifted_params)
+static Score shifted(const Score & p)
+{
+  Score q = p;
+  int smax = 0;
+  for (int i = 0; i < 16; i++) { for (int j = 0; j < 16; j++) { smax = std::max<int>(smax, p.S[i][j]); } }
+  int const c = (smax + 1) / 2;
+  q.shift = c;
+  for (int i = 0; i < 16; i++) { for (int j = 0; j < 16; j++) { q.S[i][j] = static_cast<int16_t>(p.S[i][j] - 2 * c); } }
+  for (int k = 0; k < 6; k++) { q.ge[k] = p.ge[k] + c; }
+  q.match = p.match - 2 * c; q.mismatch = p.mismatch - 2 * c;
+  return q;
 }
 
 // forward pass of one (query, target) in plain ints, checkpoints written into half `half` of the task arrays
@@ -72,11 +89,11 @@ static int forward(const Score & sp, const std::vector<uint8_t> & q, const std::
       f_in = f > hf ? f : hf;
       int const l = i / R, r = i % R;
       if (r == R - 1) {   // leaves lane l's last row: what lane l hands down at step j + l
-        U2 & ck = rowck[static_cast<size_t>(j + l) * 32 + l];
+        U2 & ck = rowck[row_index(j + l, l)];
         put(ck.x, h); put(ck.y, f_in);
       }
-      if ((j + 1) % KC == 0) {
-        U2 & ck = colck[(static_cast<size_t>((j + 1) / KC) * 32 + l) * R + r];
+      if ((j + l + 1) % CHUNK == 0) {   // the lane's state at the end of a 32-step chunk
+        U2 & ck = colck[col_index((j + l + 1) / CHUNK, l, r, R)];
         put(ck.x, h); put(ck.y, ein[i]);
       }
     }
@@ -115,10 +132,11 @@ int main(int argc, char ** argv)
       for (int z = 0; z < 6; z++) { sc.v[2 + z] = rng() % 22; sc.v[8 + z] = rng() % 4; }
     }
     sc.n_mismatch = (k % 7 == 6);
-    Score sp; build(sc, sp);
+    Score sp0; build(sc, sp0);
+    Score const sp = shifted(sp0);
     const char * A = (k % 5 == 4) ? iupac : acgt;
     size_t const na = std::strlen(A);
-    int const R = 1 + rng() % 8;
+    int const R = 1 + rng() % 16;
     int const Q = 1 + rng() % (32 * R);            // single strip
     std::string qs(Q, 'A');
     for (auto & ch : qs) { ch = A[rng() % na]; }
@@ -129,8 +147,8 @@ int main(int argc, char ** argv)
       for (int x = 0; x < D; x++) { ts[h][x] = (k % 2 == 0 && x < Q && rng() % 10 != 0) ? qs[x] : A[rng() % na]; }
     }
     int const dmax = static_cast<int>(std::max(ts[0].size(), ts[1].size()));
-    std::vector<U2> rowck(static_cast<size_t>(dmax + 31) * 32, U2{0xdeaddeadu, 0xdeaddeadu});
-    std::vector<U2> colck(static_cast<size_t>(dmax / KC + 2) * 32 * R, U2{0xdeaddeadu, 0xdeaddeadu});
+    std::vector<U2> rowck(static_cast<size_t>((dmax + 31 + 3) / 4) * 128, U2{0xdeaddeadu, 0xdeaddeadu});
+    std::vector<U2> colck(static_cast<size_t>((dmax + 31 + CHUNK - 1) / CHUNK) * 32 * R, U2{0xdeaddeadu, 0xdeaddeadu});
     std::vector<uint8_t> q4(Q);
     for (int i = 0; i < Q; i++) { q4[i] = oracle_map_4bit(static_cast<unsigned char>(qs[i])); }
     for (int h = 0; h < 2; h++) {
@@ -144,10 +162,15 @@ int main(int argc, char ** argv)
         int const DD = static_cast<int>(ts[hh].size());
         std::vector<uint8_t> tt(DD);
         for (int x = 0; x < DD; x++) { tt[x] = oracle_map_4bit(static_cast<unsigned char>(ts[hh][x])); }
-        PairView pv{rowck.data(), colck.data(), R, hh, Q, DD, q4.data(), tt.data()};
+        int general = 0;
+        for (int x = 0; x < Q; x++) { general |= __builtin_popcount(q4[x] & 15) != 1; }
+        for (int x = 0; x < DD; x++) { general |= __builtin_popcount(tt[x] & 15) != 1; }
+        PairView pv{rowck.data(), colck.data(), R, hh, Q, DD, general, q4.data(), tt.data()};
         TbOut out{};
         std::string rev;
-        traceback(sp, pv, out, [&](char o) { rev.push_back(o); });
+        HostBits bits;
+        if (R <= 8) { traceback<8>(sp, pv, bits, out, [&](char o) { rev.push_back(o); }); }
+        else { traceback<16>(sp, pv, bits, out, [&](char o) { rev.push_back(o); }); }
         int16_t os; uint16_t oa, om, omi, og;
         std::vector<char> cig(Q + DD + 64);
         if (oracle_nw16(&sc, qs.data(), Q, ts[hh].data(), DD, &os, &oa, &om, &omi, &og, cig.data(), cig.size()) != 0) { std::fprintf(stderr, "oracle_nw16 failed\n"); return 2; }
@@ -174,7 +197,7 @@ int main(int argc, char ** argv)
           int const want_right = o1 == 'D' ? l1 : (o1 == 'I' ? -l1 : 0);
           ok = ok && out.trim_left == want_left && out.trim_right == want_right;
         }
-        if (hh == 1) { ok = ok && score == os; }
+        if (hh == 1) { ok = ok && score + sp.shift * (Q + DD) == os; }
         if (!ok) {
           if (++bad <= 5) {
             std::fprintf(stderr, "MISMATCH case %d half %d R %d Q %d D %d: %s vs %s  (%d %d %d %d | %d %d %d %d)\n", k, hh, R, Q, DD,

@@ -103,6 +103,10 @@ __global__ void dpx_selftest_kernel(int * bad, int a0, int a1, int b0, int b1, i
   m = __vibmax_u16x2(pk2(c0, d1), pk2(d0, c1), &ph, &pl);
   if (m != pk2(-3, -10) || !pl || ph) { b |= 2; }
   if (__vadd2(pk2(c0, 100), pk2(d1, -7)) != pk2(-1, 93)) { b |= 4; }
+  // the fused forms of the checkpoint kernel: per-half wrapping add, unsigned max (VIADDMNMX.U16x2, VIMNMX3.U16x2)
+  // lo: max(0xfffd + 0xfff6 (= -3 - 10 -> 0xfff3), 0x0002) = 0xfff3 ; hi: max(100 - 4, 96 + 1) = 97
+  if (__viaddmax_u16x2(pk2(c0, 100), pk2(c1, d0), pk2(d1, 97)) != pk2(-13, 97)) { b |= 8; }
+  if (__vimax3_u16x2(pk2(a0, a1), pk2(b0, b1), pk2(d1, c1)) != pk2(7, -10)) { b |= 16; }
   *bad = b;
 }
 
@@ -711,6 +715,7 @@ __global__ void traceback_kernel(const __grid_constant__ ScoreParams sp, DevSeqs
   int const p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npairs) { return; }
   PairDesc const pd = pairs[p];
+  if (pd.kind == 2) { return; }  // checkpoint layout: traceback_ckpt_pairs_kernel's (align_ckpt.cuh)
   traceback_one<TEXT>(sp, qs, ts, pd, dir, cigar_scratch, stats);
 }
 

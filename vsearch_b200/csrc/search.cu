@@ -280,6 +280,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   for (int t = 0; t < nthreads; t++) {
     c->children[static_cast<size_t>(t)]->dir_budget = std::max<size_t>(c->dir_budget / static_cast<size_t>(nthreads), static_cast<size_t>(1) << 30);
     c->children[static_cast<size_t>(t)]->fast_disabled = c->fast_disabled;
+    c->children[static_cast<size_t>(t)]->ckpt_enabled = c->ckpt_enabled;
   }
 
   vsg_ctx * const parent = c;
@@ -795,6 +796,7 @@ extern "C" int vsg_allpairs(vsg_ctx * c, const vsg_seqset * set, int64_t row0, i
   for (int t = 0; t < nthreads; t++) {
     c->children[static_cast<size_t>(t)]->dir_budget = std::max<size_t>(c->dir_budget / static_cast<size_t>(nthreads), static_cast<size_t>(1) << 30);
     c->children[static_cast<size_t>(t)]->fast_disabled = c->fast_disabled;
+    c->children[static_cast<size_t>(t)]->ckpt_enabled = c->ckpt_enabled;
   }
   std::vector<std::vector<vsg_pair_hit>> out(static_cast<size_t>(nblocks));
   std::vector<int64_t> bpairs(static_cast<size_t>(nblocks), 0), bcells(static_cast<size_t>(nblocks), 0);

@@ -2,6 +2,7 @@
 // entry point vsg_align_pairs (replaces search16_init/qprep/search16/exit,
 // reference core/align_simd.cpp:1282-2060; see include/vsg.h for the per-function mapping).
 #include "align_kernels.cuh"
+#include "align_ckpt.cuh"
 
 #include <cub/cub.cuh>
 
@@ -134,6 +135,24 @@ static void build_score_params(const vsg_scoring & s, ScoreParams & p)
   p.score_min = static_cast<int16_t>(-32768 + gpmax);  // align_simd.cpp:1432-1444
 }
 
+// The shifted scoring of the checkpoint kernels (align_ckpt.cuh): c = ceil(smax / 2), S2 = S - 2c <= 0, ge2 = ge + c.
+// Same alignment problem, every cell of anti-diagonal i+j lowered by c*(i+j+2); false if a value leaves int16.
+static bool shifted_params(const ScoreParams & p, ScoreParams & q)
+{
+  q = p;
+  int smax = 0;
+  for (int i = 0; i < 16; i++) { for (int j = 0; j < 16; j++) { smax = std::max<int>(smax, p.S[i][j]); } }
+  int const c = (smax + 1) / 2;
+  q.shift = c;
+  bool ok = true;
+  auto fit = [&](int v) -> int16_t { if (v < -32767 || v > 32767) { ok = false; } return static_cast<int16_t>(v); };
+  for (int i = 0; i < 16; i++) { for (int j = 0; j < 16; j++) { q.S[i][j] = fit(p.S[i][j] - 2 * c); } }
+  for (int k = 0; k < 6; k++) { q.ge[k] = fit(p.ge[k] + c); }
+  q.match = fit(p.match - 2 * c);
+  q.mismatch = fit(p.mismatch - 2 * c);
+  return ok;
+}
+
 // search16_fits, align_simd.cpp:130-134
 static inline bool fits16(int64_t q, int64_t d) { return (q + d <= 65535) && (q * d <= 25000000LL); }
 
@@ -206,6 +225,9 @@ extern "C" int vsg_ctx_create(int device, const vsg_scoring * scoring, vsg_ctx *
   c->device = device;
   c->scoring = *scoring;
   build_score_params(*scoring, c->sp);
+  c->sp.shift = 0;
+  c->ckpt_enabled = shifted_params(c->sp, c->sp2);
+  if (const char * ck = std::getenv("VSG_CKPT")) { if (ck[0] == '0') { c->ckpt_enabled = false; } }
   const char * df = std::getenv("VSG_DISABLE_FAST");
   c->fast_disabled = (df != nullptr && df[0] == '1');
   const char * db = std::getenv("VSG_DIR_BUDGET_MB");
@@ -430,8 +452,61 @@ void launch_fast(vsg_ctx * c, int R, bool general, bool multi, const DevSeqs & q
   }
 }
 
+// checkpoint forward kernel (align_ckpt.cuh): plain-ACGT tasks use the per-lane profile up to 8 rows per lane and
+// the lane-replicated table above; tasks with IUPAC symbols the 16x16x16 table at 4, 8 or 16 rows per lane
+template <int R, int MODE>
+void launch_ckpt_one(vsg_ctx * c, const DevSeqs & qs, const DevSeqs & ts, const FastTask * d_tasks, int n)
+{
+  int const blocks = (n + FAST_WARPS - 1) / FAST_WARPS;
+  constexpr size_t dyn = ck_dyn_smem(R, MODE);
+  if (dyn > 48 * 1024) {
+    cudaFuncSetAttribute(nw_ckpt_kernel<R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn));
+  }
+  nw_ckpt_kernel<R, MODE><<<blocks, FAST_WARPS * 32, dyn, c->stream>>>(
+      c->sp2, qs, ts, d_tasks, n, static_cast<uint2 *>(c->dir.p), static_cast<uint2 *>(c->bnd.p),
+      static_cast<int32_t *>(c->stats.p));
+  count_launch();
+}
+
+void launch_ckpt(vsg_ctx * c, int R, bool general, const DevSeqs & qs, const DevSeqs & ts, const FastTask * d_tasks, int n)
+{
+  if (general) {
+    switch (R) {
+      case 4: launch_ckpt_one<4, CK_GEN>(c, qs, ts, d_tasks, n); break;
+      case 8: launch_ckpt_one<8, CK_GEN>(c, qs, ts, d_tasks, n); break;
+      default: launch_ckpt_one<16, CK_GEN>(c, qs, ts, d_tasks, n); break;
+    }
+    return;
+  }
+  switch (R) {
+#define VSG_CASE(r) case r: launch_ckpt_one<r, CK_PROF>(c, qs, ts, d_tasks, n); break;
+    VSG_CASE(1) VSG_CASE(2) VSG_CASE(3) VSG_CASE(4) VSG_CASE(5) VSG_CASE(6) VSG_CASE(7) VSG_CASE(8)
+#undef VSG_CASE
+#define VSG_CASE(r) case r: launch_ckpt_one<r, CK_LUT>(c, qs, ts, d_tasks, n); break;
+    VSG_CASE(9) VSG_CASE(10) VSG_CASE(11) VSG_CASE(12) VSG_CASE(13) VSG_CASE(14) VSG_CASE(15)
+    default: launch_ckpt_one<16, CK_LUT>(c, qs, ts, d_tasks, n); break;
+#undef VSG_CASE
+  }
+}
+
+void launch_tb_ckpt_tasks(vsg_ctx * c, int R, bool general, const DevSeqs & qs, const DevSeqs & ts, const FastTask * d_tasks, int n)
+{
+  int const nthr = 2 * n;
+  int const blocks = (nthr + TB_CK_THREADS - 1) / TB_CK_THREADS;
+  if (R <= 8) {
+    traceback_ckpt_tasks_kernel<8><<<blocks, TB_CK_THREADS, 0, c->stream>>>(
+        c->sp2, qs, ts, d_tasks, n, R, general ? 1 : 0, static_cast<const uint2 *>(c->dir.p), static_cast<const uint2 *>(c->bnd.p),
+        static_cast<int32_t *>(c->stats.p));
+  } else {
+    traceback_ckpt_tasks_kernel<16><<<blocks, TB_CK_THREADS, 0, c->stream>>>(
+        c->sp2, qs, ts, d_tasks, n, R, general ? 1 : 0, static_cast<const uint2 *>(c->dir.p), static_cast<const uint2 *>(c->bnd.p),
+        static_cast<int32_t *>(c->stats.p));
+  }
+  count_launch();
+}
+
 // A chunk = the tasks whose direction blocks share the scratch buffer at the same time.
-struct ClassRun { int R; bool general, multi; size_t first; int count; };  // a run of one kernel class in all_fast
+struct ClassRun { int R; bool general, multi, ckpt; size_t first; int count; };  // a run of one kernel class in all_fast
 struct ChunkPlan {
   std::vector<ClassRun> runs;
   size_t exact_first = 0; int exact_count = 0;
@@ -441,7 +516,7 @@ struct ChunkPlan {
 };
 
 struct ChunkBuilder {  // the chunk being filled
-  std::vector<FastTask> fast[2][2][FAST_RMAX + 1];  // [general][several strips][rows per lane]
+  std::vector<FastTask> fast[2][3][FAST_RMAX + 1];  // [general][0 = one strip, direction bits; 1 = several strips; 2 = checkpoints][rows per lane]
   std::vector<ExactTask> exact;
   uint64_t dir_bytes = 0, bnd_elems = 0, he_elems = 0, cigar_bytes = 0;
   int64_t cells = 0, nfast = 0, nexact = 0;
@@ -485,6 +560,7 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
 
   ScoreParams const & sp = c->sp;
   FastBound const fbound = fast_bound_of(sp);
+  FastBound const fbound2 = fast_bound_of(c->sp2);
   std::vector<FastTask> all_fast;
   std::vector<ExactTask> all_exact;
   std::vector<PairDesc> all_pairs;  // CIGAR mode only
@@ -504,15 +580,15 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
   auto close_chunk = [&]() {
     if (cb.empty()) { return; }
     ChunkPlan pl;
-    for (int gm = 0; gm < 4; gm++) {
-      int const g = gm >> 1, m = gm & 1;
+    for (int gm = 0; gm < 6; gm++) {
+      int const g = gm / 3, m = gm % 3;
       for (int R = 1; R <= FAST_RMAX; R++) {
         auto & v = cb.fast[g][m][R];
         if (v.empty()) { continue; }
         // longest first: the tail of the grid is made of the short ones
         auto const longer = [](const FastTask & a, const FastTask & b) { return a.dmax > b.dmax; };
         if (!std::is_sorted(v.begin(), v.end(), longer)) { std::sort(v.begin(), v.end(), longer); }
-        pl.runs.push_back(ClassRun{R, g != 0, m != 0, all_fast.size(), static_cast<int>(v.size())});
+        pl.runs.push_back(ClassRun{R, g != 0, m == 1, m == 2, all_fast.size(), static_cast<int>(v.size())});
         all_fast.insert(all_fast.end(), v.begin(), v.end());
         v.clear();
       }
@@ -528,11 +604,11 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
     cb.cells = cb.nfast = cb.nexact = 0; cb.npairdesc = 0;
   };
 
-  auto add_pairdesc = [&](uint32_t q, uint32_t t, int kind, int64_t slot, int R, int half, int dmax, uint64_t dir_off) {
+  auto add_pairdesc = [&](uint32_t q, uint32_t t, int kind, int64_t slot, int R, int half, int dmax, uint64_t dir_off, uint64_t aux_off = 0) {
     if (!want_cigar) { return; }
     PairDesc pd{};
     pd.q = q; pd.t = t; pd.dir_off = dir_off; pd.kind = kind; pd.out = static_cast<int32_t>(slot);
-    pd.R = R; pd.half = half; pd.dmax = dmax;
+    pd.R = R; pd.half = half; pd.dmax = dmax; pd.aux_off = aux_off;
     pd.cigar_off = cb.cigar_bytes;
     cb.cigar_bytes += static_cast<uint64_t>(queries->h_len[q]) + static_cast<uint64_t>(targets->h_len[t]) + 2;
     all_pairs.push_back(pd);
@@ -603,20 +679,25 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
         int R, ns;
         fast_shape(Q, a.general, R, ns);
         int const dmax = std::max(a.d, b.d);
-        uint64_t const dirb = static_cast<uint64_t>(ns) * fast_strip_bytes(dmax, R);
-        if (!cb.empty() && cb.dir_bytes + dirb > c->dir_budget) { close_chunk(); }
+        // single-strip tasks go through the checkpoint kernel (no direction bits; align_ckpt.cuh) when its
+        // shifted scoring stays inside the exact range too
+        bool const ck = (ns == 1) && c->ckpt_enabled && fast_path_ok(fbound2, 32 * R, dmax);
+        uint64_t const dirb = ck ? ck_row_elems(dmax) * sizeof(uint2) : static_cast<uint64_t>(ns) * fast_strip_bytes(dmax, R);
+        uint64_t const auxe = ck ? ck_col_elems(dmax, R) : (ns > 1 ? static_cast<uint64_t>(dmax) : 0);
+        if (!cb.empty() && cb.dir_bytes + dirb + (cb.bnd_elems + auxe) * sizeof(uint2) > c->dir_budget) { close_chunk(); }
         FastTask ft{};
         ft.q = q; ft.tlo = a.t; ft.thi = b.t;
         ft.out_lo = static_cast<int32_t>(a.slot);
         ft.out_hi = pair2 ? static_cast<int32_t>(b.slot) : -1;
         ft.dmax = dmax;
-        ft.dir_off = cb.dir_bytes;
+        ft.dir_off = ck ? cb.dir_bytes / sizeof(uint2) : cb.dir_bytes;   // checkpoints: uint2 element offsets
         ft.bnd_off = cb.bnd_elems;
-        add_pairdesc(q, a.t, 0, a.slot, R, 0, dmax, cb.dir_bytes);
-        if (pair2) { add_pairdesc(q, b.t, 0, b.slot, R, 1, dmax, cb.dir_bytes); }
-        cb.dir_bytes += dirb;
-        if (ns > 1) { cb.bnd_elems += static_cast<uint64_t>(dmax); }
-        cb.fast[a.general ? 1 : 0][ns > 1 ? 1 : 0][R].push_back(ft);
+        int const gbit = a.general ? 2 : 0;
+        add_pairdesc(q, a.t, ck ? 2 : 0, a.slot, R, ck ? gbit : 0, dmax, ft.dir_off, ft.bnd_off);
+        if (pair2) { add_pairdesc(q, b.t, ck ? 2 : 0, b.slot, R, ck ? (gbit | 1) : 1, dmax, ft.dir_off, ft.bnd_off); }
+        cb.dir_bytes += align_up(dirb, 32);
+        cb.bnd_elems += auxe;
+        cb.fast[a.general ? 1 : 0][ck ? 2 : (ns > 1 ? 1 : 0)][R].push_back(ft);
         cb.cells += static_cast<int64_t>(Q) * a.d + (pair2 ? static_cast<int64_t>(Q) * b.d : 0);
         cb.nfast += pair2 ? 2 : 1;
         k += pair2 ? 2 : 1;
@@ -666,7 +747,10 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
   for (size_t ci = 0; ci < plans.size(); ci++) {
     ChunkPlan const & pl = plans[ci];
     VSG_CUDA_OK(cudaEventRecord(c->ev_pool[3 * ci], c->stream));
-    for (auto const & run : pl.runs) { launch_fast(c, run.R, run.general, run.multi, queries->d, targets->d, d_fast + run.first, run.count); }
+    for (auto const & run : pl.runs) {
+      if (run.ckpt) { launch_ckpt(c, run.R, run.general, queries->d, targets->d, d_fast + run.first, run.count); }
+      else { launch_fast(c, run.R, run.general, run.multi, queries->d, targets->d, d_fast + run.first, run.count); }
+    }
     if (pl.exact_count > 0) {
       nw_exact_kernel<<<(pl.exact_count + 63) / 64, 64, 0, c->stream>>>(sp, queries->d, targets->d, d_exact + pl.exact_first,
                                                                         pl.exact_count, d_dir, static_cast<int16_t *>(c->he.p), d_stats);
@@ -675,6 +759,7 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
     VSG_CUDA_OK(cudaEventRecord(c->ev_pool[3 * ci + 1], c->stream));
     if (!want_cigar) {
       for (auto const & run : pl.runs) {
+        if (run.ckpt) { launch_tb_ckpt_tasks(c, run.R, run.general, queries->d, targets->d, d_fast + run.first, run.count); continue; }
         int const nthr = 2 * run.count;
         traceback_fast_tasks_kernel<<<(nthr + 127) / 128, 128, 0, c->stream>>>(sp, queries->d, targets->d, d_fast + run.first,
                                                                                run.count, run.R, d_dir, d_stats);
@@ -700,6 +785,19 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
       traceback_kernel<true><<<(np + 127) / 128, 128, 0, c->stream>>>(sp, queries->d, targets->d, d_pairs, np, d_dir,
                                                                       static_cast<char *>(c->cigar_scratch.p), d_stats);
       count_launch();
+      bool ck8 = false, ck16 = false;
+      for (auto const & run : pl.runs) { if (run.ckpt) { (run.R <= 8 ? ck8 : ck16) = true; } }
+      int const tbb = (np + TB_CK_THREADS - 1) / TB_CK_THREADS;
+      if (ck8) {
+        traceback_ckpt_pairs_kernel<8><<<tbb, TB_CK_THREADS, 0, c->stream>>>(c->sp2, queries->d, targets->d, d_pairs, np,
+            static_cast<const uint2 *>(c->dir.p), static_cast<const uint2 *>(c->bnd.p), static_cast<char *>(c->cigar_scratch.p), d_stats);
+        count_launch();
+      }
+      if (ck16) {
+        traceback_ckpt_pairs_kernel<16><<<tbb, TB_CK_THREADS, 0, c->stream>>>(c->sp2, queries->d, targets->d, d_pairs, np,
+            static_cast<const uint2 *>(c->dir.p), static_cast<const uint2 *>(c->bnd.p), static_cast<char *>(c->cigar_scratch.p), d_stats);
+        count_launch();
+      }
       VSG_CUDA_OK(cudaEventRecord(c->ev_pool[3 * ci + 2], c->stream));
       cigar_len_kernel<<<(np + 255) / 256, 256, 0, c->stream>>>(d_pairs, d_stats, np, static_cast<int64_t *>(c->cigar_len.p));
       count_launch();

@@ -25,6 +25,7 @@ struct ScoreParams {
   int16_t score_min;  // SHRT_MIN + max(0, all six open+extend) (align_simd.cpp:1432-1444)
   int16_t n_mismatch;
   int32_t fallback;   // a value did not fit a 16-bit cell: every pair is deferred
+  int32_t shift;      // anti-diagonal shift c of a SHIFTED scoring (align_ckpt.cuh): S - 2c, ge + c; 0 = the caller's own
 };
 
 // One symbol per byte in HBM: bits 0-3 = 4-bit IUPAC code (utils/maps.cpp:75-118),
@@ -61,12 +62,13 @@ struct ExactTask {
 struct PairDesc {
   uint32_t q, t;
   uint64_t dir_off;
-  int32_t kind;   // 0 = fast layout, 1 = exact layout
+  int32_t kind;   // 0 = fast layout, 1 = exact layout, 2 = checkpoints (align_ckpt.cuh): dir_off / aux_off are uint2 element offsets
   int32_t out;    // pair slot in the stats array
   int32_t R;      // fast: rows per lane
-  int32_t half;   // fast: 0 = low nibble, 1 = high nibble
+  int32_t half;   // fast: 0 = low nibble, 1 = high nibble; checkpoints: bit 0 = half, bit 1 = general alphabet
   int32_t dmax;   // fast: steps per strip = dmax + 31
   uint64_t cigar_off;  // scratch region for the reversed CIGAR (qlen+dlen+2 bytes)
+  uint64_t aux_off;    // checkpoints: element offset of the task's column checkpoints
 };
 
 struct Error {
@@ -114,6 +116,8 @@ struct vsg_ctx {
   cudaStream_t stream = nullptr;
   vsg_scoring scoring{};
   vsg::ScoreParams sp{};
+  vsg::ScoreParams sp2{};      // the shifted scoring the checkpoint kernels run with (align_ckpt.cuh)
+  bool ckpt_enabled = true;    // VSG_CKPT=0 routes single-strip pairs through the direction-bit kernel instead (A/B, tests)
   bool fast_disabled = false;  // VSG_DISABLE_FAST=1 (tests force the exact kernel)
   // scratch
   vsg::DevBuf dir, bnd, he, cigar_scratch, cigar_dense, stats, tasks_fast, tasks_exact, pairs,
