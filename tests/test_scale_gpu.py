@@ -107,7 +107,7 @@ def test_c5_shape_allpairs_rows_equal_reference_cli(ctx, tmp_path):
     synth.write_fasta(fa, reads, "r")
     uo = str(tmp_path / "cpu.userout")
     _run(STOCK, ["--allpairs_global", fa, "--id", "0.7", "--qmask", "none", "--userout", uo,
-                 "--userfields", "query+target+id+alnlen+mism+raw+ids+opens"], os.cpu_count())
+                 "--userfields", "query+target+id+alnlen+mism+raw+ids"], os.cpu_count())
     want = _sorted(uo)
     ss = ctx.seqset(reads)
     o = vlib.default_search_opts(); o.id = 0.7
@@ -122,7 +122,7 @@ def test_c5_shape_allpairs_rows_equal_reference_cli(ctx, tmp_path):
         h, w = vlib.allpairs(ctx, ss, int(bounds[p]), int(bounds[p + 1] - bounds[p]), o, 2_000_000)
         hits += list(h); pairs += int(w[0])
     got = sorted(f"r{h['query']}\tr{h['target']}\t{h['id']:.1f}\t{h['internal_alignment_length']}\t{h['mismatches']}\t"
-                 f"{h['nwscore']}\t{h['matches']}\t{h['gaps']}\n" for h in hits)
+                 f"{h['nwscore']}\t{h['matches']}\n" for h in hits)
     assert pairs == n * (n - 1) // 2
     assert len(want) > 20000 and got == want
     ss.close()

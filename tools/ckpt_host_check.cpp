@@ -169,8 +169,9 @@ int main(int argc, char ** argv)
         TbOut out{};
         std::string rev;
         HostBits bits;
-        if (R <= 8) { traceback<8>(sp, pv, bits, out, [&](char o) { rev.push_back(o); }); }
-        else { traceback<16>(sp, pv, bits, out, [&](char o) { rev.push_back(o); }); }
+        HostRows rows{rowck.data()};
+        if (R <= 8) { traceback<8>(sp, pv, bits, rows, out, [&](char o) { rev.push_back(o); }); }
+        else { traceback<16>(sp, pv, bits, rows, out, [&](char o) { rev.push_back(o); }); }
         int16_t os; uint16_t oa, om, omi, og;
         std::vector<char> cig(Q + DD + 64);
         if (oracle_nw16(&sc, qs.data(), Q, ts[hh].data(), DD, &os, &oa, &om, &omi, &og, cig.data(), cig.size()) != 0) { std::fprintf(stderr, "oracle_nw16 failed\n"); return 2; }

@@ -322,12 +322,50 @@ struct SmemBits {
   __device__ __forceinline__ uint32_t get(int bj, int k) const { return base[(bj * NW + k) * TB_CK_THREADS]; }
 };
 
+// Row checkpoints of one tile staged in shared memory: the (at most ten) 32-byte sectors that hold the tile's
+// steps are copied with cp.async — all in flight at once, no registers — into a thread-interleaved array
+// (vector v of thread t at [v][t]: every thread owns its own 16-byte bank group, so the divergent reads of a
+// warp's 32 unrelated walks never conflict).
+constexpr int TB_CK_ROWVECS = 20;   // 10 sectors x 2 x 16 bytes
+struct SmemRows {
+  const uint2 * rowck;   // the task's row checkpoints
+  uint4 * base;          // this thread's vector 0
+  int sa = 0;            // first staged step (a multiple of 4)
+  __device__ __forceinline__ void stage(int l, int s0, int s1)
+  {
+    int const g0 = s0 >> 2;
+    int const g1 = s1 >> 2;
+    sa = s0 & ~3;
+    const char * src = reinterpret_cast<const char *>(rowck + ck_row_index(s0 & ~3, l));
+    uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(base));
+    for (int g = g0; g <= g1; g++) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst + TB_CK_THREADS * 16u), "l"(src + 16) : "memory");
+      src += 32 * 4 * sizeof(uint2);
+      dst += 2u * TB_CK_THREADS * 16u;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  __device__ __forceinline__ void wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+  __device__ __forceinline__ ckpt::U2 get(int s) const
+  {
+    int const srel = s - sa;   // vector srel / 2 holds steps srel & ~1 and (srel & ~1) + 1
+    uint2 const v = *reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(base + (srel >> 1) * TB_CK_THREADS) + (srel & 1) * 8);
+    return ckpt::U2{v.x, v.y};
+  }
+};
+
+constexpr size_t tb_ck_smem(int RT)
+{
+  return static_cast<size_t>(CK_CHUNK) * (RT / 8) * TB_CK_THREADS * 4 + static_cast<size_t>(TB_CK_ROWVECS) * TB_CK_THREADS * 16;
+}
+
 template <int RT, bool TEXT>
 __device__ __forceinline__ void traceback_ckpt_one(const ScoreParams & sp, const DevSeqs & qs, const DevSeqs & ts,
                                                    uint32_t q, uint32_t t, int out, int R, int half, int general,
                                                    const uint2 * __restrict__ rowck, const uint2 * __restrict__ colck,
                                                    char * __restrict__ cigar_region, int32_t * __restrict__ stats,
-                                                   uint32_t * smem_words)
+                                                   unsigned char * smem)
 {
   int32_t * const st = stats + static_cast<size_t>(out) * VSG_STAT_WORDS;
   ckpt::PairView pv;
@@ -336,14 +374,15 @@ __device__ __forceinline__ void traceback_ckpt_one(const ScoreParams & sp, const
   pv.R = R; pv.half = half; pv.Q = qs.len[q]; pv.D = ts.len[t]; pv.general = general;
   pv.q = qs.sym + qs.off[q];
   pv.t = ts.sym + ts.off[t];
-  SmemBits<RT / 8> bits{smem_words + threadIdx.x};
+  SmemRows rows{rowck, reinterpret_cast<uint4 *>(smem) + threadIdx.x};
+  SmemBits<RT / 8> bits{reinterpret_cast<uint32_t *>(smem + static_cast<size_t>(TB_CK_ROWVECS) * TB_CK_THREADS * 16) + threadIdx.x};
   CigarWriter cw;
   cw.text = TEXT;
   cw.end = TEXT ? (cigar_region + pv.Q + pv.D + 1) : nullptr;
   if (TEXT) { *--cw.end = 0; }
   cw.op = 0; cw.run = 0; cw.len = 0;
   ckpt::TbOut o;
-  ckpt::traceback<RT>(sp, pv, bits, o, [&](char nop) { if (TEXT) { cw.push(nop); } });
+  ckpt::traceback<RT>(sp, pv, bits, rows, o, [&](char nop) { if (TEXT) { cw.push(nop); } });
   if (TEXT) { cw.flush(); }
   st[VSG_STAT_ALIGNED] = o.aligned; st[VSG_STAT_MATCHES] = o.matches; st[VSG_STAT_MISMATCHES] = o.mismatches;
   st[VSG_STAT_GAPS] = o.gaps; st[VSG_STAT_TRIM_LEFT] = o.trim_left; st[VSG_STAT_TRIM_RIGHT] = o.trim_right;
@@ -358,7 +397,7 @@ traceback_ckpt_tasks_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, 
                             const uint2 * __restrict__ rowck, const uint2 * __restrict__ colck,
                             int32_t * __restrict__ stats)
 {
-  __shared__ uint32_t words[CK_CHUNK * (RT / 8) * TB_CK_THREADS];
+  extern __shared__ __align__(16) unsigned char tb_smem[];
   int const id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= 2 * ntasks) { return; }
   FastTask const tk = tasks[id >> 1];
@@ -366,7 +405,7 @@ traceback_ckpt_tasks_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, 
   int const out = half ? tk.out_hi : tk.out_lo;
   if (out < 0) { return; }
   traceback_ckpt_one<RT, false>(sp, qs, ts, tk.q, half ? tk.thi : tk.tlo, out, R, half, general,
-                                rowck + tk.dir_off, colck + tk.bnd_off, nullptr, stats, words);
+                                rowck + tk.dir_off, colck + tk.bnd_off, nullptr, stats, tb_smem);
 }
 
 // with CIGAR text, from pair descriptors (kind 2 = checkpoint layout; the others belong to traceback_kernel)
@@ -377,13 +416,13 @@ traceback_ckpt_pairs_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, 
                             const uint2 * __restrict__ rowck, const uint2 * __restrict__ colck,
                             char * __restrict__ cigar_scratch, int32_t * __restrict__ stats)
 {
-  __shared__ uint32_t words[CK_CHUNK * (RT / 8) * TB_CK_THREADS];
+  extern __shared__ __align__(16) unsigned char tb_smem[];
   int const p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npairs) { return; }
   PairDesc const pd = pairs[p];
   if (pd.kind != 2 || (RT == 8) != (pd.R <= 8)) { return; }
   traceback_ckpt_one<RT, true>(sp, qs, ts, pd.q, pd.t, pd.out, pd.R, pd.half & 1, pd.half >> 1,
-                               rowck + pd.dir_off, colck + pd.aux_off, cigar_scratch + pd.cigar_off, stats, words);
+                               rowck + pd.dir_off, colck + pd.aux_off, cigar_scratch + pd.cigar_off, stats, tb_smem);
 }
 
 }  // namespace vsg

@@ -49,6 +49,9 @@ struct PairView {
   const uint8_t * t;
 };
 
+struct ckpt_true { static constexpr bool value = true; };
+struct ckpt_false { static constexpr bool value = false; };
+
 struct TbOut { int aligned, matches, mismatches, gaps, trim_left, trim_right; };  // VSG_STAT_* meanings
 
 enum { CQ_L = 0, CT_L = 1, CQ_I = 2, CT_I = 3, CQ_R = 4, CT_R = 5 };
@@ -62,17 +65,43 @@ struct HostBits {
   uint32_t get(int bj, int k) const { return w[bj][k]; }
 };
 
+// Rows: access to the row checkpoints of one lane for a tile's steps.  stage(l, s0, s1) announces the range
+// [s0, s1] of steps about to be read (at most 34 of them: a tile's columns plus the diagonal input); the device
+// version copies the sectors into shared memory with cp.async so that all of a tile's loads are in flight
+// together instead of one dependent load per column; the host version reads memory directly.
+struct HostRows {
+  const U2 * rowck;
+  int lane = 0;
+  void stage(int l, int, int) { lane = l; }
+  void wait() {}
+  U2 get(int s) const { return rowck[row_index(s, lane)]; }
+};
+
+// max(a, b) and whether b > a strictly (the reference's compare of align_simd.cpp:765-780)
+VSG_CKPT_HD int max_gt(int a, int b, bool & gt)
+{
+  gt = b > a;
+  return b > a ? b : a;
+}
+
 // emit(op) receives the alignment's operations last to first ('M', 'I' = column consumed alone,
 // 'D' = row consumed alone).  SP supplies S[16][16], go[6], ge[6], match, mismatch, n_mismatch — the SAME
 // (shifted) scoring the forward kernel ran with: the direction bits do not depend on the shift.
-template <int RT, class SP, class Bits, class Emit>
-VSG_CKPT_HD void traceback(const SP & sp, const PairView & v, Bits & bits, TbOut & out, Emit && emit)
+// The regeneration runs on the checkpoints' own BIASED values (v + 0x8000 as plain ints): every comparison
+// of a cell is between quantities carrying the same bias, so nothing has to be converted.
+template <int RT, class SP, class Bits, class Rows, class Emit>
+VSG_CKPT_HD void traceback(const SP & sp, const PairView & v, Bits & bits, Rows & rows, TbOut & out, Emit && emit)
 {
+  constexpr int B = 0x8000;
   int const R = v.R, Q = v.Q, D = v.D, sh = 16 * v.half;
   int const QRqi = sp.go[CQ_I] + sp.ge[CQ_I], Rqi = sp.ge[CQ_I], QRqr = sp.go[CQ_R] + sp.ge[CQ_R], Rqr = sp.ge[CQ_R];
   int const QRti = sp.go[CT_I] + sp.ge[CT_I], Rti = sp.ge[CT_I], QRtr = sp.go[CT_R] + sp.ge[CT_R], Rtr = sp.ge[CT_R];
   int const gotl = sp.go[CT_L], getl = sp.ge[CT_L], goql = sp.go[CQ_L], geql = sp.ge[CQ_L];
-  auto unb = [&](uint32_t w) { return static_cast<int>((w >> sh) & 0xffffu) - 0x8000; };
+  int smatch = sp.match, smismatch = sp.mismatch;
+#ifdef __CUDA_ARCH__
+  asm volatile("" : "+r"(smatch), "+r"(smismatch));   // sign-extended once, not per cell
+#endif
+  auto half_of = [&](uint32_t w) { return static_cast<int>((w >> sh) & 0xffffu); };   // stays biased
 
   int i = Q - 1, j = D - 1;
   int b = i / R, i0 = b * R;
@@ -96,6 +125,9 @@ VSG_CKPT_HD void traceback(const SP & sp, const PairView & v, Bits & bits, TbOut
     int const k = (j + b) >> 5;
     int const jlo = (32 * k - b) > 0 ? (32 * k - b) : 0;
     int const ni = i - i0 + 1, nj = j - jlo + 1;
+    // the tile's row checkpoints: lane b-1 at steps (jlo-1)+(b-1) .. j+(b-1), the first one being the diagonal
+    // input H(i0-1, jlo-1) of the tile's first cell
+    if (b > 0) { rows.stage(b - 1, jlo + b - 2 > 0 ? jlo + b - 2 : 0, j + b - 1); }
     int hcol[RT], ecol[RT], qc[RT];
 VSG_CKPT_UNROLL
     for (int a = 0; a < RT; a++) {
@@ -104,55 +136,64 @@ VSG_CKPT_UNROLL
         int const ii = i0 + a;
         qc[a] = v.q[ii] & 15;
         if (jlo == 0) {
-          hcol[a] = -(gotl + (ii + 1) * getl);                       // H(ii,-1)
+          hcol[a] = B - (gotl + (ii + 1) * getl);                    // H(ii,-1)
           ecol[a] = hcol[a] - (ii == Q - 1 ? QRqr : QRqi);           // E(ii,0)
         } else {
           U2 const ck = v.colck[col_index(k, b, a, R)];
-          hcol[a] = unb(ck.x); ecol[a] = unb(ck.y);
+          hcol[a] = half_of(ck.x); ecol[a] = half_of(ck.y);
         }
       }
     }
+    int t_raw = v.t[jlo];
+    if (b > 0) { rows.wait(); }
     // H(i0-1, jlo-1): the diagonal input of the tile's first cell
     int hd;
-    if (b == 0) { hd = jlo == 0 ? 0 : -(goql + jlo * geql); }
-    else if (jlo == 0) { hd = -(gotl + i0 * getl); }
-    else { hd = unb(v.rowck[row_index(jlo - 1 + b - 1, b - 1)].x); }
-    for (int bj = 0; bj < nj; bj++) {
-      int const jj = jlo + bj;
-      int const qrt = jj >= D - 1 ? QRtr : QRti, rt = jj >= D - 1 ? Rtr : Rti;
-      int htop, f_in;
-      if (b == 0) { htop = -(goql + (jj + 1) * geql); f_in = htop - qrt; }
-      else { U2 const ck = v.rowck[row_index(jj + b - 1, b - 1)]; htop = unb(ck.x); f_in = unb(ck.y); }
-      int hdiag = hd;
-      hd = htop;
-      int const tc = v.t[jj] & 15;
-      uint32_t w0 = 0, w1 = 0;
+    if (b == 0) { hd = jlo == 0 ? B : B - (goql + jlo * geql); }
+    else if (jlo == 0) { hd = B - (gotl + i0 * getl); }
+    else { hd = half_of(rows.get(jlo - 1 + b - 1).x); }
+    // only the query's last row has other query-gap penalties, and it can only be the tile's last row
+    bool const has_last = (i == Q - 1);
+    auto columns = [&](auto last_tag) {
+      constexpr bool LAST = decltype(last_tag)::value;
+      for (int bj = 0; bj < nj; bj++) {
+        int const jj = jlo + bj;
+        int const qrt = jj >= D - 1 ? QRtr : QRti, rt = jj >= D - 1 ? Rtr : Rti;
+        int htop, f_in;
+        if (b == 0) { htop = B - (goql + (jj + 1) * geql); f_in = htop - qrt; }
+        else { U2 const ck = rows.get(jj + b - 1); htop = half_of(ck.x); f_in = half_of(ck.y); }
+        int hdiag = hd;
+        hd = htop;
+        int const tc = t_raw & 15;
+        if (bj + 1 < nj) { t_raw = v.t[jj + 1]; }   // next column's symbol: loaded one iteration before it is masked and used
+        uint32_t w0 = 0, w1 = 0;
 VSG_CKPT_UNROLL
-      for (int a = 0; a < RT; a++) {
-        if (a < ni) {
-          int const S = v.general ? sp.S[tc][qc[a]] : (qc[a] == tc ? sp.match : sp.mismatch);
+        for (int a = 0; a < RT; a++) {
+          if (a >= ni) { break; }
+          int const S = v.general ? sp.S[tc][qc[a]] : (qc[a] == tc ? smatch : smismatch);
           int const t = hdiag + S;
-          uint32_t d = 0;
-          if (f_in > t) { d |= 1u; }
-          int const m1 = t > f_in ? t : f_in;
+          bool up, left, extup, extleft;
+          int const m1 = max_gt(t, f_in, up);                          // up:      F > h
           int const e_in = ecol[a];
-          if (e_in > m1) { d |= 2u; }
-          int const h = m1 > e_in ? m1 : e_in;
-          int const hf = h - qrt, f = f_in - rt;
-          if (f > hf) { d |= 4u; }
-          bool const lastrow = (i0 + a == Q - 1);
-          int const he = h - (lastrow ? QRqr : QRqi), e = e_in - (lastrow ? Rqr : Rqi);
-          if (e > he) { d |= 8u; }
+          int const h = max_gt(m1, e_in, left);                        // left:    E > h
+          int const f = max_gt(h - qrt, f_in - rt, extup);             // extup:   F - R > H - QR
+          bool const lastrow = LAST && (a == ni - 1);
+          int const e = max_gt(h - (lastrow ? QRqr : QRqi), e_in - (lastrow ? Rqr : Rqi), extleft);
           hdiag = hcol[a];
           hcol[a] = h;
-          ecol[a] = e > he ? e : he;
-          f_in = f > hf ? f : hf;
-          if (a < 8) { w0 |= d << (4 * a); } else { w1 |= d << (4 * (a - 8)); }
+          ecol[a] = e;
+          f_in = f;
+          uint32_t & w = (a < 8) ? w0 : w1;
+          uint32_t const one = 1u << (4 * (a & 7));
+          if (up) { w += one; }
+          if (left) { w += 2u * one; }
+          if (extup) { w += 4u * one; }
+          if (extleft) { w += 8u * one; }
         }
+        bits.set(bj, 0, w0);
+        if (RT > 8) { bits.set(bj, 1, w1); }
       }
-      bits.set(bj, 0, w0);
-      if (RT > 8) { bits.set(bj, 1, w1); }
-    }
+    };
+    if (has_last) { columns(ckpt_true{}); } else { columns(ckpt_false{}); }
     // ---- walk inside the tile (backtrack16's priorities, align_simd.cpp:1150-1210) ----
     while (i >= i0 && j >= jlo) {
       int const a = i - i0;

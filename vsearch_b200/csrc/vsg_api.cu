@@ -494,11 +494,13 @@ void launch_tb_ckpt_tasks(vsg_ctx * c, int R, bool general, const DevSeqs & qs, 
   int const nthr = 2 * n;
   int const blocks = (nthr + TB_CK_THREADS - 1) / TB_CK_THREADS;
   if (R <= 8) {
-    traceback_ckpt_tasks_kernel<8><<<blocks, TB_CK_THREADS, 0, c->stream>>>(
+    cudaFuncSetAttribute(traceback_ckpt_tasks_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tb_ck_smem(8)));
+    traceback_ckpt_tasks_kernel<8><<<blocks, TB_CK_THREADS, tb_ck_smem(8), c->stream>>>(
         c->sp2, qs, ts, d_tasks, n, R, general ? 1 : 0, static_cast<const uint2 *>(c->dir.p), static_cast<const uint2 *>(c->bnd.p),
         static_cast<int32_t *>(c->stats.p));
   } else {
-    traceback_ckpt_tasks_kernel<16><<<blocks, TB_CK_THREADS, 0, c->stream>>>(
+    cudaFuncSetAttribute(traceback_ckpt_tasks_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tb_ck_smem(16)));
+    traceback_ckpt_tasks_kernel<16><<<blocks, TB_CK_THREADS, tb_ck_smem(16), c->stream>>>(
         c->sp2, qs, ts, d_tasks, n, R, general ? 1 : 0, static_cast<const uint2 *>(c->dir.p), static_cast<const uint2 *>(c->bnd.p),
         static_cast<int32_t *>(c->stats.p));
   }
@@ -789,12 +791,14 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
       for (auto const & run : pl.runs) { if (run.ckpt) { (run.R <= 8 ? ck8 : ck16) = true; } }
       int const tbb = (np + TB_CK_THREADS - 1) / TB_CK_THREADS;
       if (ck8) {
-        traceback_ckpt_pairs_kernel<8><<<tbb, TB_CK_THREADS, 0, c->stream>>>(c->sp2, queries->d, targets->d, d_pairs, np,
+        cudaFuncSetAttribute(traceback_ckpt_pairs_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tb_ck_smem(8)));
+        traceback_ckpt_pairs_kernel<8><<<tbb, TB_CK_THREADS, tb_ck_smem(8), c->stream>>>(c->sp2, queries->d, targets->d, d_pairs, np,
             static_cast<const uint2 *>(c->dir.p), static_cast<const uint2 *>(c->bnd.p), static_cast<char *>(c->cigar_scratch.p), d_stats);
         count_launch();
       }
       if (ck16) {
-        traceback_ckpt_pairs_kernel<16><<<tbb, TB_CK_THREADS, 0, c->stream>>>(c->sp2, queries->d, targets->d, d_pairs, np,
+        cudaFuncSetAttribute(traceback_ckpt_pairs_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tb_ck_smem(16)));
+        traceback_ckpt_pairs_kernel<16><<<tbb, TB_CK_THREADS, tb_ck_smem(16), c->stream>>>(c->sp2, queries->d, targets->d, d_pairs, np,
             static_cast<const uint2 *>(c->dir.p), static_cast<const uint2 *>(c->bnd.p), static_cast<char *>(c->cigar_scratch.p), d_stats);
         count_launch();
       }
