@@ -263,6 +263,32 @@ int vsg_allpairs(vsg_ctx * ctx, const vsg_seqset * set, int64_t row0, int64_t nr
                  const vsg_search_opts * opts, vsg_pair_hit * hits, int64_t cap, int64_t * nhits,
                  int64_t * work);
 
+/* ---- several GPUs behind one process (the reference is a single process, LIBRARY_API.md:138-156):
+ *      vsg_group_create uploads the database ONCE (to devices[0]; dust_db != 0 also DUST-masks it there,
+ *      core/mask.cpp dust_all), copies the packed sequences device to device over NVLink to every other GPU and
+ *      builds the k-mer index on each.  vsg_group_search shards the queries (host arrays, as for
+ *      vsg_seqset_create) into contiguous ranges of equal nucleotide count, one per device, and runs
+ *      vsg_search_batch on all devices concurrently; results land in the caller's arrays in query order.
+ *      vsg_group_allpairs shards the rows of the group's own sequence set with vsg_allpairs_partition.  No
+ *      collective is involved beyond the one-to-all copy of the database.  stats: ms3 = {upload+mask on the first
+ *      device, device-to-device copies, index builds}, bytes copied between devices. ---- */
+typedef struct vsg_group vsg_group;
+int vsg_group_create(const int * devices, int ndev, const vsg_scoring * scoring, const char * cat,
+                     const int64_t * off, const int32_t * len, int64_t n, int wordlength, int mask_lower,
+                     int dust_db, vsg_group ** out);
+void vsg_group_destroy(vsg_group * g);
+int vsg_group_size(const vsg_group * g);
+vsg_ctx * vsg_group_ctx(vsg_group * g, int i);
+vsg_seqset * vsg_group_db(vsg_group * g, int i);
+vsg_index * vsg_group_index(vsg_group * g, int i);
+int vsg_group_stats(const vsg_group * g, double * ms3, int64_t * broadcast_bytes);
+int vsg_group_set_fallback(vsg_group * g, vsg_fallback_fn fn, void * user);
+int vsg_group_search(vsg_group * g, const char * qcat, const int64_t * qoff, const int32_t * qlen, int64_t nq,
+                     int dust_queries, const vsg_search_opts * opts, vsg_search_result * results, int max_results,
+                     int32_t * counts, int64_t * work);
+int vsg_group_allpairs(vsg_group * g, const vsg_search_opts * opts, vsg_pair_hit * hits, int64_t cap,
+                       int64_t * nhits, int64_t * work);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,10 +40,23 @@ namespace {
   std::abort();
 }
 
-int device_ordinal()
+// VSG_DEVICES=0,1,2,... : the GPUs this process may use (queries are sharded across them); default: VSG_DEVICE or 0
+std::vector<int> device_list()
 {
-  const char * e = std::getenv("VSG_DEVICE");
-  return e != nullptr ? std::atoi(e) : 0;
+  std::vector<int> d;
+  if (const char * e = std::getenv("VSG_DEVICES")) {
+    const char * p = e;
+    while (*p != '\0') {
+      d.push_back(std::atoi(p));
+      while (*p != '\0' && *p != ',') { ++p; }
+      if (*p == ',') { ++p; }
+    }
+  }
+  if (d.empty()) {
+    const char * e = std::getenv("VSG_DEVICE");
+    d.push_back(e != nullptr ? std::atoi(e) : 0);
+  }
+  return d;
 }
 
 // The database and its index are shared read-only objects of the embedding application
@@ -56,17 +69,13 @@ struct Mirror {
   unsigned int wordlength = 0;
   int mask_lower = 0;
   vsg_scoring scoring{};
-  vsg_ctx * ctx = nullptr;
-  vsg_seqset * set = nullptr;
-  vsg_index * index = nullptr;
+  vsg_group * group = nullptr;   // one context + database copy + index per device
   std::vector<int64_t> sizes;    // db.getabundance
   std::vector<int64_t> labels;   // header identity: equal numbers <=> equal headers
   std::unordered_map<std::string, int64_t> label_of;
   void drop()
   {
-    if (index != nullptr) { vsg_index_destroy(index); index = nullptr; }
-    if (set != nullptr) { vsg_seqset_destroy(set); set = nullptr; }
-    if (ctx != nullptr) { vsg_ctx_destroy(ctx); ctx = nullptr; }
+    if (group != nullptr) { vsg_group_destroy(group); group = nullptr; }
     sizes.clear(); labels.clear(); label_of.clear();
   }
 };
@@ -95,12 +104,11 @@ Mirror & mirror_of(Parameters const & p, Dbindex const & dbindex, Database const
   char const * const first = n > 0 ? db.getsequence(0) : nullptr;
   vsg_scoring const sc = scoring_of(p);
   int const mask_lower = (p.opt_dbmask != Masking::none) ? 1 : 0;
-  if (m.ctx != nullptr && m.db == &db && m.count == n && m.first == first && m.nucleotides == db.getnucleotidecount() &&
+  if (m.group != nullptr && m.db == &db && m.count == n && m.first == first && m.nucleotides == db.getnucleotidecount() &&
       m.wordlength == dbindex.wordlength && m.mask_lower == mask_lower && std::memcmp(&m.scoring, &sc, sizeof sc) == 0) {
     return m;
   }
   m.drop();
-  if (vsg_ctx_create(device_ordinal(), &sc, &m.ctx) != VSG_OK) { die("vsg_ctx_create"); }
   std::vector<int64_t> off(n);
   std::vector<int32_t> len(n);
   uint64_t total = 0;
@@ -113,8 +121,10 @@ Mirror & mirror_of(Parameters const & p, Dbindex const & dbindex, Database const
     auto const it = m.label_of.emplace(std::string(db.getheader(i)), static_cast<int64_t>(m.label_of.size()));
     m.labels[i] = it.first->second;
   }
-  if (vsg_seqset_create(m.ctx, cat.data(), off.data(), len.data(), static_cast<int64_t>(n), 1, &m.set) != VSG_OK) { die("vsg_seqset_create(database)"); }
-  if (vsg_index_create(m.ctx, m.set, static_cast<int>(dbindex.wordlength), mask_lower, &m.index) != VSG_OK) { die("vsg_index_create"); }
+  // one upload, device-to-device copies to the other GPUs, an index per GPU (the database arrives already masked)
+  std::vector<int> const devs = device_list();
+  if (vsg_group_create(devs.data(), static_cast<int>(devs.size()), &sc, cat.data(), off.data(), len.data(), static_cast<int64_t>(n),
+                       static_cast<int>(dbindex.wordlength), mask_lower, 0, &m.group) != VSG_OK) { die("vsg_group_create"); }
   m.db = &db; m.count = n; m.first = first; m.nucleotides = db.getnucleotidecount();
   m.wordlength = dbindex.wordlength; m.mask_lower = mask_lower; m.scoring = sc;
   return m;
@@ -234,10 +244,6 @@ auto search_batch(struct Parameters const & parameters,
       std::memcpy(cat.data() + off[i], tmp.data(), static_cast<size_t>(len[i]));
     }
   }
-  vsg_seqset * q = nullptr;
-  if (vsg_seqset_create(m.ctx, cat.data(), off.data(), len.data(), query_count, 1, &q) != VSG_OK) { die("vsg_seqset_create(queries)"); }
-  if (p.opt_qmask == Masking::dust && vsg_seqset_dust(m.ctx, q) != VSG_OK) { die("vsg_seqset_dust"); }
-
   vsg_search_opts o;
   vsg_search_opts_default(&o);
   o.id = p.opt_id; o.weak_id = p.opt_weak_id;
@@ -270,27 +276,19 @@ auto search_batch(struct Parameters const & parameters,
     o.target_labels = m.labels.data();
   }
 
-  // deferred pairs: the masked query text the reference would hand to its LinearMemoryAligner
+  // deferred pairs: the query text the reference would hand to its LinearMemoryAligner (case is immaterial there)
   std::vector<std::string> masked(nq);
-  {
-    std::vector<uint8_t> sym(static_cast<size_t>(total) + 1);
-    if (vsg_seqset_symbols(m.ctx, q, sym.data(), total + 1) != VSG_OK) { die("vsg_seqset_symbols"); }
-    for (size_t i = 0; i < nq; i++) {
-      masked[i].assign(cat.data() + off[i], static_cast<size_t>(len[i]));
-      for (int k = 0; k < len[i]; k++) {
-        char & ch = masked[i][static_cast<size_t>(k)];
-        bool const lower = (sym[static_cast<size_t>(off[i] + k)] & 16) != 0;
-        if (p.opt_qmask == Masking::dust) { ch = static_cast<char>(lower ? (ch | 32) : (ch & ~32)); }
-      }
-    }
-  }
+  for (size_t i = 0; i < nq; i++) { masked[i].assign(cat.data() + off[i], static_cast<size_t>(len[i])); }
   FallbackEnv env{&p, &db, &masked};
-  vsg_ctx_set_fallback(m.ctx, lma_fallback, &env);
+  vsg_group_set_fallback(m.group, lma_fallback, &env);
 
   std::vector<vsg_search_result> r(nq * static_cast<size_t>(max_results_per_query));
-  int const rc = vsg_search_batch(m.ctx, m.index, m.set, q, 0, query_count, &o, r.data(), max_results_per_query, result_counts, nullptr);
-  vsg_ctx_set_fallback(m.ctx, nullptr, nullptr);
-  if (rc != VSG_OK) { vsg_seqset_destroy(q); die("vsg_search_batch"); }
+  // queries: one packed host buffer; every device uploads its contiguous share, DUST-masks it on the device
+  // (search.cpp:437-449) and searches it
+  int const rc = vsg_group_search(m.group, cat.data(), off.data(), len.data(), query_count, p.opt_qmask == Masking::dust ? 1 : 0,
+                                  &o, r.data(), max_results_per_query, result_counts, nullptr);
+  vsg_group_set_fallback(m.group, nullptr, nullptr);
+  if (rc != VSG_OK) { die("vsg_group_search"); }
   for (size_t i = 0; i < nq; i++) {
     for (int j = 0; j < result_counts[i]; j++) {
       vsg_search_result const & x = r[i * static_cast<size_t>(max_results_per_query) + static_cast<size_t>(j)];
@@ -300,5 +298,4 @@ auto search_batch(struct Parameters const & parameters,
       y.accepted = x.accepted != 0; y.strand = x.strand;
     }
   }
-  vsg_seqset_destroy(q);
 }

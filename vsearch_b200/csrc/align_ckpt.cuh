@@ -28,7 +28,11 @@
 
 namespace vsg {
 
-constexpr int CK_CHUNK = 32;   // steps per chunk = distance between column checkpoints (in steps)
+#ifndef VSG_CK_CHUNK
+#define VSG_CK_CHUNK 32
+#endif
+constexpr int CK_CHUNK = VSG_CK_CHUNK;   // steps per chunk = distance between column checkpoints (in steps): 16 or 32
+static_assert(CK_CHUNK == 16 || CK_CHUNK == 32, "chunk");
 
 // ---- checkpoint layout of one task (uint2 elements; .x/.y = the two values, low half = first target) ----
 // row checkpoints: element of (step s, lane l) — four consecutive steps of a lane share a 32-byte sector
@@ -210,16 +214,16 @@ nw_ckpt_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
     nxt_a = (cc < Dlo) ? (dlo_p[cc] & 15) : 0;
     nxt_b = (cc < Dhi) ? (dhi_p[cc] & 15) : 0;
   };
-  if (lane < dmax) { fetch(lane); }
+  if (lane < CK_CHUNK && lane < dmax) { fetch(lane); }
 
   int const cap_lo = Dlo - 1 + llast, cap_hi = Dhi - 1 + llast;
   uint32_t const geql2 = pk1(geql);
   for (int s0 = 0; s0 < nsteps; s0 += CK_CHUNK) {
     {
-      // publish columns [s0, s0+32): one column per lane; then start loading the next chunk's symbols
+      // publish columns [s0, s0+CHUNK): one column per lane; then start loading the next chunk's symbols
       __syncwarp();
       int const cc = s0 + lane;
-      if (cc < dmax) {
+      if (lane < CK_CHUNK && cc < dmax) {
         uint32_t x; uint2 yz;
         make_record(cc, nxt_a, nxt_b, x, yz);
         int const slot = cc & (RING - 1);
@@ -227,14 +231,15 @@ nw_ckpt_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
         rA[slot] = yz; rA[slot + RING] = yz;
       }
       __syncwarp();
-      if (cc + CK_CHUNK < dmax) { fetch(cc + CK_CHUNK); }
+      if (lane < CK_CHUNK && cc + CK_CHUNK < dmax) { fetch(cc + CK_CHUNK); }
     }
     uint32_t const slot0 = static_cast<uint32_t>(s0 - lane) & (RING - 1);
     // STEADY chunk: all 32 lanes inside the matrix, no score to pick up, and the target-gap penalties
     // uniform over the chunk's columns (neither target's last column is inside [s0-31, s0+31])
-    bool const steady = (s0 >= 32) && (s0 + 31 < dmax) &&
-                        (static_cast<unsigned>(cap_lo - s0) >= 32u) && (static_cast<unsigned>(cap_hi - s0) >= 32u) &&
-                        (static_cast<unsigned>(Dlo - 1 - (s0 - 31)) >= 63u) && (static_cast<unsigned>(Dhi - 1 - (s0 - 31)) >= 63u);
+    constexpr unsigned CH = CK_CHUNK;
+    bool const steady = (s0 >= 32) && (s0 + CK_CHUNK - 1 < dmax) &&
+                        (static_cast<unsigned>(cap_lo - s0) >= CH) && (static_cast<unsigned>(cap_hi - s0) >= CH) &&
+                        (static_cast<unsigned>(Dlo - 1 - (s0 - 31)) >= 31u + CH) && (static_cast<unsigned>(Dhi - 1 - (s0 - 31)) >= 31u + CH);
     if (steady) {
       bool const lo_done = (s0 - 31 > Dlo - 1), hi_done = (s0 - 31 > Dhi - 1);
       uint32_t const yneg = pk2(-(lo_done ? QRtr : QRti), -(hi_done ? QRtr : QRti));
@@ -326,7 +331,7 @@ struct SmemBits {
 // steps are copied with cp.async — all in flight at once, no registers — into a thread-interleaved array
 // (vector v of thread t at [v][t]: every thread owns its own 16-byte bank group, so the divergent reads of a
 // warp's 32 unrelated walks never conflict).
-constexpr int TB_CK_ROWVECS = 20;   // 10 sectors x 2 x 16 bytes
+constexpr int TB_CK_ROWVECS = 2 * ((CK_CHUNK + 8) / 4);   // sectors of CHUNK + 2 steps at any alignment, x 2 x 16 bytes
 struct SmemRows {
   const uint2 * rowck;   // the task's row checkpoints
   uint4 * base;          // this thread's vector 0

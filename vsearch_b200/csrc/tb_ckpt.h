@@ -31,7 +31,10 @@
 namespace vsg {
 namespace ckpt {
 
-constexpr int CHUNK = 32;   // CK_CHUNK of align_ckpt.cuh
+#ifndef VSG_CK_CHUNK
+#define VSG_CK_CHUNK 32
+#endif
+constexpr int CHUNK = VSG_CK_CHUNK;   // CK_CHUNK of align_ckpt.cuh
 constexpr int RMAX = 16;    // rows per lane
 
 struct U2 { uint32_t x, y; };  // layout of CUDA's uint2
@@ -122,8 +125,8 @@ VSG_CKPT_HD void traceback(const SP & sp, const PairView & v, Bits & bits, Rows 
 
   while (i >= 0 && j >= 0) {
     // ---- regenerate the tile (lane b, chunk k) up to the cell (i, j) ----
-    int const k = (j + b) >> 5;
-    int const jlo = (32 * k - b) > 0 ? (32 * k - b) : 0;
+    int const k = (j + b) / CHUNK;
+    int const jlo = (CHUNK * k - b) > 0 ? (CHUNK * k - b) : 0;
     int const ni = i - i0 + 1, nj = j - jlo + 1;
     // the tile's row checkpoints: lane b-1 at steps (jlo-1)+(b-1) .. j+(b-1), the first one being the diagonal
     // input H(i0-1, jlo-1) of the tile's first cell
@@ -152,9 +155,8 @@ VSG_CKPT_UNROLL
     else if (jlo == 0) { hd = B - (gotl + i0 * getl); }
     else { hd = half_of(rows.get(jlo - 1 + b - 1).x); }
     // only the query's last row has other query-gap penalties, and it can only be the tile's last row
-    bool const has_last = (i == Q - 1);
-    auto columns = [&](auto last_tag) {
-      constexpr bool LAST = decltype(last_tag)::value;
+    int const alast = (i == Q - 1) ? ni - 1 : -1;
+    {
       for (int bj = 0; bj < nj; bj++) {
         int const jj = jlo + bj;
         int const qrt = jj >= D - 1 ? QRtr : QRti, rt = jj >= D - 1 ? Rtr : Rti;
@@ -176,7 +178,7 @@ VSG_CKPT_UNROLL
           int const e_in = ecol[a];
           int const h = max_gt(m1, e_in, left);                        // left:    E > h
           int const f = max_gt(h - qrt, f_in - rt, extup);             // extup:   F - R > H - QR
-          bool const lastrow = LAST && (a == ni - 1);
+          bool const lastrow = (a == alast);
           int const e = max_gt(h - (lastrow ? QRqr : QRqi), e_in - (lastrow ? Rqr : Rqi), extleft);
           hdiag = hcol[a];
           hcol[a] = h;
@@ -192,8 +194,7 @@ VSG_CKPT_UNROLL
         bits.set(bj, 0, w0);
         if (RT > 8) { bits.set(bj, 1, w1); }
       }
-    };
-    if (has_last) { columns(ckpt_true{}); } else { columns(ckpt_false{}); }
+    }
     // ---- walk inside the tile (backtrack16's priorities, align_simd.cpp:1150-1210) ----
     while (i >= i0 && j >= jlo) {
       int const a = i - i0;

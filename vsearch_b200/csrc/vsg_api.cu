@@ -478,6 +478,8 @@ void launch_ckpt(vsg_ctx * c, int R, bool general, const DevSeqs & qs, const Dev
     }
     return;
   }
+  static const bool force_lut = std::getenv("VSG_CK_LUT") != nullptr;   // experiment: table variant (more resident warps) for R <= 8 too
+  if (force_lut && R == 8) { launch_ckpt_one<8, CK_LUT>(c, qs, ts, d_tasks, n); return; }
   switch (R) {
 #define VSG_CASE(r) case r: launch_ckpt_one<r, CK_PROF>(c, qs, ts, d_tasks, n); break;
     VSG_CASE(1) VSG_CASE(2) VSG_CASE(3) VSG_CASE(4) VSG_CASE(5) VSG_CASE(6) VSG_CASE(7) VSG_CASE(8)

@@ -14,7 +14,7 @@ from typing import List, Optional
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(ROOT, "vsearch_b200", "csrc", "libvsg.so")
+LIB_PATH = os.environ.get("VSG_LIB") or os.path.join(ROOT, "vsearch_b200", "csrc", "libvsg.so")   # VSG_LIB: an experimental build (A/B runs)
 HEADER = os.path.join(ROOT, "include", "vsg.h")
 
 DEFAULT_PEN = (2, -4, 1, 1, 18, 18, 1, 1, 1, 1, 2, 2, 1, 1)
@@ -90,6 +90,9 @@ def load():
     lib.vsg_launch_count.restype = C.c_int64
     lib.vsg_ctx_stream.restype = C.c_void_p
     lib.vsg_seqset_count.restype = C.c_int64
+    lib.vsg_group_ctx.restype = C.c_void_p
+    lib.vsg_group_db.restype = C.c_void_p
+    lib.vsg_group_index.restype = C.c_void_p
     _lib = lib
     return lib
 
@@ -298,6 +301,61 @@ def allpairs(ctx: "Context", ss: SeqSetHandle, row0: int, nrows: int, opts: Sear
                                hits.ctypes.data_as(C.POINTER(PairHit)), C.c_int64(cap), C.byref(n),
                                _ptr(work, C.c_int64)), "vsg_allpairs")
     return hits[: n.value], work
+
+
+class Group:
+    """vsg_group: one process, several GPUs (database copied device to device, queries / rows sharded)"""
+
+    def __init__(self, devices, ss, wordlength=8, mask_lower=0, dust_db=0, pen=DEFAULT_PEN, n_mismatch=0):
+        lib = load()
+        sc = Scoring()
+        for i in range(14):
+            sc.v[i] = int(pen[i])
+        sc.n_mismatch = int(n_mismatch)
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        cat = np.ascontiguousarray(ss.cat, dtype=np.uint8)
+        offs = np.ascontiguousarray(ss.offs, dtype=np.int64)
+        lens = np.ascontiguousarray(ss.lens, dtype=np.int32)
+        self.h = C.c_void_p()
+        self.n = int(lens.shape[0])
+        _check(lib.vsg_group_create(_ptr(dev, C.c_int), C.c_int(dev.shape[0]), C.byref(sc), _ptr(cat, C.c_char),
+                                    _ptr(offs, C.c_int64), _ptr(lens, C.c_int32), C.c_int64(self.n), C.c_int(wordlength),
+                                    C.c_int(mask_lower), C.c_int(dust_db), C.byref(self.h)), "vsg_group_create")
+
+    def close(self):
+        if self.h:
+            load().vsg_group_destroy(self.h)
+            self.h = None
+
+    def stats(self):
+        ms = np.zeros(3, dtype=np.float64)
+        b = C.c_int64()
+        _check(load().vsg_group_stats(self.h, _ptr(ms, C.c_double), C.byref(b)), "vsg_group_stats")
+        return {"upload_ms": float(ms[0]), "broadcast_ms": float(ms[1]), "index_ms": float(ms[2]), "broadcast_bytes": int(b.value)}
+
+    def search(self, qs, opts: SearchOpts, max_results: int, dust_queries: int = 0):
+        nq = len(qs)
+        res = (SearchResult * (nq * max_results))()
+        counts = np.zeros(nq, dtype=np.int32)
+        work = np.zeros(4, dtype=np.int64)
+        cat = np.ascontiguousarray(qs.cat, dtype=np.uint8)
+        offs = np.ascontiguousarray(qs.offs, dtype=np.int64)
+        lens = np.ascontiguousarray(qs.lens, dtype=np.int32)
+        _check(load().vsg_group_search(self.h, _ptr(cat, C.c_char), _ptr(offs, C.c_int64), _ptr(lens, C.c_int32),
+                                       C.c_int64(nq), C.c_int(dust_queries), C.byref(opts), res, C.c_int(max_results),
+                                       _ptr(counts, C.c_int32), _ptr(work, C.c_int64)), "vsg_group_search")
+        return res, counts, work
+
+    def allpairs(self, opts: SearchOpts, cap: int):
+        dt = np.dtype([("query", np.int32), ("target", np.int32), ("matches", np.int32), ("mismatches", np.int32),
+                       ("gaps", np.int32), ("alignment_length", np.int32), ("nwscore", np.int32),
+                       ("internal_alignment_length", np.int32), ("id", np.float64)])
+        hits = np.zeros(cap, dtype=dt)
+        n = C.c_int64()
+        work = np.zeros(2, dtype=np.int64)
+        _check(load().vsg_group_allpairs(self.h, C.byref(opts), hits.ctypes.data_as(C.POINTER(PairHit)), C.c_int64(cap),
+                                         C.byref(n), _ptr(work, C.c_int64)), "vsg_group_allpairs")
+        return hits[: n.value], work
 
 
 def default_search_opts() -> SearchOpts:
