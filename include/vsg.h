@@ -263,6 +263,34 @@ int vsg_allpairs(vsg_ctx * ctx, const vsg_seqset * set, int64_t row0, int64_t nr
                  const vsg_search_opts * opts, vsg_pair_hit * hits, int64_t cap, int64_t * nhits,
                  int64_t * work);
 
+/* ---- greedy centroid clustering: replaces cluster_core_parallel / cluster_core_serial with cluster_query_core,
+ *      evaluate_extra_hits and Dbindex::add_sequence (core/cluster.cpp:162-189, 601-856, 877-1115;
+ *      core/dbindex.cpp:121-148) for --cluster_fast-style clustering of `set` IN THE ORDER GIVEN (the reference
+ *      sorts by decreasing length first, core/db.cpp:433-449; mask the set with vsg_seqset_dust and pass
+ *      opts->mask_lower = 1 for the default --qmask dust).  round_size = the reference's --threads: sequences are
+ *      searched in rounds of that many against the centroids found so far and then resolved one by one, centroids
+ *      of the same round included (cluster.cpp:881-882, 946-1025) — the assignments depend on it, so compare
+ *      with `vsearch --cluster_fast --threads round_size`.  results[i] for sequence i: its cluster number
+ *      (creation order of the centroids) and either centroid = -1 (it founded the cluster: an "S" record of
+ *      --uc) or the sequence number of the centroid it matched plus that alignment's statistics and identity
+ *      (an "H" record; the CIGAR is one vsg_align_pairs call away).  opts: id, iddef, maxaccepts, maxrejects,
+ *      wordlength, minwordmatches, mask_lower, the length / abundance / post-alignment filters (target_sizes
+ *      and target_labels are per sequence of `set`); plus strand only.  work (optional, 2 x int64): pairs and DP
+ *      cells handed to the aligner. ---- */
+typedef struct vsg_cluster_result {
+  int32_t cluster;
+  int32_t centroid;
+  int32_t matches;
+  int32_t mismatches;
+  int32_t gaps;
+  int32_t alignment_length;
+  int32_t nwscore;
+  int32_t strand;
+  double id;
+} vsg_cluster_result;
+int vsg_cluster_fast(vsg_ctx * ctx, const vsg_seqset * set, const vsg_search_opts * opts, int round_size,
+                     vsg_cluster_result * results, int64_t * nclusters, int64_t * work);
+
 /* ---- several GPUs behind one process (the reference is a single process, LIBRARY_API.md:138-156):
  *      vsg_group_create uploads the database ONCE (to devices[0]; dust_db != 0 also DUST-masks it there,
  *      core/mask.cpp dust_all), copies the packed sequences device to device over NVLink to every other GPU and

@@ -38,10 +38,14 @@ constexpr uint16_t POST_PAD = 0x8000;   // list padding: counts into a dummy cou
 constexpr int COUNTER_WORDS = SHARD / 2 + 1;
 
 struct ShardDev {
-  const uint32_t * start;  // 4^k + 1
-  const uint16_t * post;
+  const uint32_t * start;  // 4^k + 1 list offsets (incremental index: where this shard's part of every list begins)
+  const uint16_t * post;   // shard-local target numbers (static index)
   int32_t t0;              // first target of the shard
   int32_t nt;              // targets in the shard
+  // incremental index (cluster driver): lists of 32-bit target numbers in creation order, this shard's part of
+  // list km is post32[start[km] .. end[km])
+  const uint32_t * end;
+  const uint32_t * post32;
 };
 
 __device__ __forceinline__ bool sym_bad(int s, int mask_lower)
@@ -151,6 +155,7 @@ __device__ __forceinline__ uint64_t make_key(uint32_t count, uint32_t len, uint3
          static_cast<uint64_t>(0xffffffu - seqno);
 }
 
+template <bool INCR>
 __global__ void __launch_bounds__(RANK_THREADS)
 rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restrict__ shards, int nshards,
             int k, int mask_lower, int minwordmatches, int tophits,
@@ -274,7 +279,7 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
       for (int i = threadIdx.x; i < np2; i += blockDim.x) {
         uint32_t const km = kmers[i];
         uint32_t b = 0, n = 0;
-        if (km != 0xffffffffu) { b = S.start[km]; n = S.start[km + 1] - b; }
+        if (km != 0xffffffffu) { b = S.start[km]; n = (INCR ? S.end[km] : S.start[km + 1]) - b; }
         lbeg[i] = b; llen[i] = n;
       }
       __syncthreads();
@@ -284,7 +289,17 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
       //    before it touches a counter: six independent HBM requests per lane hide the latency that a
       //    one-list-at-a-time loop exposes once per list (the typical list is ~70 vectors long).
       //    Padding entries land in the dummy word counters[SHARD/2].
-      {
+      if constexpr (INCR) {
+        // unpadded lists of 32-bit target numbers: one warp per list, coalesced loads
+        for (int li = warp; li < np2; li += NWARPS) {
+          uint32_t const n = llen[li];
+          const uint32_t * __restrict__ pl = S.post32 + lbeg[li];
+          for (uint32_t e = lane; e < n; e += 32) {
+            uint32_t const a = __ldg(pl + e) - static_cast<uint32_t>(S.t0);
+            atomicAdd(&counters[a >> 1], (a & 1) ? 0x10000u : 1u);
+          }
+        }
+      } else {
         auto pair_len = [&](int li) -> uint32_t {
           uint32_t const na = llen[li] >> 3;
           uint32_t const nb = (li + NWARPS < np2) ? (llen[li + NWARPS] >> 3) : 0u;
@@ -603,6 +618,7 @@ extern "C" int vsg_index_create(vsg_ctx * c, const vsg_seqset * db, int wordleng
     count_launch();
     ShardDev sd;
     sd.start = static_cast<uint32_t *>(bs.p); sd.post = static_cast<uint16_t *>(bp.p); sd.t0 = t0; sd.nt = nt;
+    sd.end = nullptr; sd.post32 = nullptr;
     ix->h_shards.push_back(sd);
     ix->total_postings += total;
   }
@@ -649,7 +665,7 @@ int rank_enqueue(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * queries, 
   VSG_CUDA_OK(cudaMemsetAsync(*d_status, 0, sizeof(int32_t), c->stream));
   if (nq == 0) { return VSG_OK; }
   cudaStream_t const rs = c->stream;
-  VSG_CUDA_OK(cudaFuncSetAttribute(rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(RANK_SMEM)));
+  VSG_CUDA_OK(cudaFuncSetAttribute(rank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(RANK_SMEM)));
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
   int const grid = static_cast<int>(std::min<int64_t>(nq, static_cast<int64_t>(sms) * 2));
@@ -665,7 +681,7 @@ int rank_enqueue(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * queries, 
     d_scratch = static_cast<uint32_t *>(c->rank_scratch.p);
   }
   VSG_CUDA_OK(cudaEventRecord(c->ev[4], rs));
-  rank_kernel<<<grid, RANK_THREADS, RANK_SMEM, rs>>>(
+  rank_kernel<false><<<grid, RANK_THREADS, RANK_SMEM, rs>>>(
       queries->d, q0, static_cast<int>(nq), ix->db->d, static_cast<const ShardDev *>(ix->b_shards.p),
       static_cast<int>(ix->h_shards.size()), ix->k, mask_lower, minwordmatches, tophits, *d_seqno, *d_count, *d_n,
       *d_status, d_scratch, stride, bitmap_words);
@@ -715,3 +731,199 @@ extern "C" int vsg_rank(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * qu
   }
   return VSG_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Incremental index of the cluster driver: replaces Dbindex::prepare + Dbindex::add_sequence
+// (core/dbindex.cpp:121-148, 163-255) for a set of targets that GROWS (the centroids).  Targets get
+// dense numbers in creation order; list km holds the numbers of the targets containing k-mer km, in
+// creation order, inside a CSR whose per-list CAPACITY is the number of sequences of the whole set that
+// contain km (every sequence could become a centroid) — counted once, as the reference's counting pass
+// does for its bitmap/list sizing.  Shards of 32768 targets are contiguous ranges of every list; the
+// list positions at a shard boundary are snapshotted when the boundary is crossed.
+// ---------------------------------------------------------------------------------------------
+namespace vsg {
+
+__global__ void cindex_append_kernel(DevSeqs db, const uint32_t * __restrict__ seqnos, int n, uint32_t first_id, int k,
+                                     int mask_lower, uint32_t * __restrict__ cursor, uint32_t * __restrict__ post32,
+                                     int32_t * __restrict__ clen)
+{
+  extern __shared__ uint32_t bitmap[];
+  int const ci = blockIdx.x;
+  if (ci >= n) { return; }
+  int const words = (1 << (2 * k)) >> 5;
+  for (int i = threadIdx.x; i < (words > 0 ? words : 1); i += blockDim.x) { bitmap[i] = 0; }
+  __syncthreads();
+  int64_t const t = seqnos[ci];
+  const uint8_t * __restrict__ s = db.sym + db.off[t];
+  int const len = db.len[t];
+  if (threadIdx.x == 0) { clen[first_id + ci] = len; }
+  for (int p = k - 1 + threadIdx.x; p < len; p += blockDim.x) {
+    uint32_t km;
+    if (kmer_at(s, p, k, mask_lower, km)) {
+      uint32_t const bit = 1u << (km & 31);
+      uint32_t const old = atomicOr(&bitmap[km >> 5], bit);
+      if ((old & bit) == 0) { post32[atomicAdd(&cursor[km], 1u)] = first_id + static_cast<uint32_t>(ci); }
+    }
+  }
+}
+
+struct CIndex {
+  int device = 0, k = 8, mask_lower = 0;
+  const vsg_seqset * set = nullptr;
+  int64_t ncent = 0;                 // targets added so far
+  DevBuf b_start, b_cursor, b_post, b_clen, b_shards, b_seqnos;
+  std::vector<DevBuf> b_begin;       // list positions at the start of shard s >= 1
+  std::vector<uint32_t> h_seqno;     // dense target number -> sequence number
+};
+
+int cindex_create(vsg_ctx * c, const vsg_seqset * set, int wordlength, int mask_lower, CIndex ** out)
+{
+  *out = nullptr;
+  if (wordlength < 3 || wordlength > 10) { Error::set("cluster index: the device index supports --wordlength 3..10"); return VSG_EINVAL; }
+  VSG_CUDA_OK(cudaSetDevice(c->device));
+  CIndex * ix = new (std::nothrow) CIndex();
+  if (ix == nullptr) { Error::set("out of host memory"); return VSG_ENOMEM; }
+  ix->device = c->device; ix->k = wordlength; ix->mask_lower = mask_lower; ix->set = set;
+  size_t const hashsize = static_cast<size_t>(1) << (2 * wordlength);
+  size_t const bitmap_bytes = std::max<size_t>(hashsize / 8, 4);
+  if (bitmap_bytes > 48 * 1024) {
+    VSG_CUDA_OK(cudaFuncSetAttribute(index_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bitmap_bytes)));
+    VSG_CUDA_OK(cudaFuncSetAttribute(cindex_append_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bitmap_bytes)));
+  }
+  int rc;
+  DevBuf cnt, tmp;
+  if ((rc = cnt.reserve(sizeof(uint32_t) * (hashsize + 1))) != VSG_OK ||
+      (rc = ix->b_start.reserve(sizeof(uint32_t) * (hashsize + 1))) != VSG_OK ||
+      (rc = ix->b_cursor.reserve(sizeof(uint32_t) * (hashsize + 1))) != VSG_OK ||
+      (rc = ix->b_clen.reserve(sizeof(int32_t) * (static_cast<size_t>(set->d.n) + 1))) != VSG_OK) { delete ix; return rc; }
+  // capacity of every list = the number of sequences of the whole set that contain the k-mer
+  VSG_CUDA_OK(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * (hashsize + 1), c->stream));
+  int64_t const n = set->d.n;
+  for (int64_t t0 = 0; t0 < n; t0 += 1 << 20) {
+    int const nt = static_cast<int>(std::min<int64_t>(1 << 20, n - t0));
+    index_build_kernel<false><<<nt, 128, bitmap_bytes, c->stream>>>(set->d, static_cast<int>(t0), nt, wordlength, mask_lower,
+                                                                    static_cast<uint32_t *>(cnt.p), nullptr, nullptr);
+    count_launch();
+  }
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, static_cast<uint32_t *>(cnt.p), static_cast<uint32_t *>(ix->b_start.p), static_cast<int>(hashsize + 1), c->stream);
+  if ((rc = tmp.reserve(tb + 16)) != VSG_OK) { delete ix; return rc; }
+  cub::DeviceScan::ExclusiveSum(tmp.p, tb, static_cast<uint32_t *>(cnt.p), static_cast<uint32_t *>(ix->b_start.p), static_cast<int>(hashsize + 1), c->stream);
+  count_launch();
+  // 64-bit check of the total: offsets are 32-bit
+  {
+    std::vector<uint32_t> h(hashsize);
+    VSG_CUDA_OK(cudaMemcpyAsync(h.data(), cnt.p, sizeof(uint32_t) * hashsize, cudaMemcpyDeviceToHost, c->stream));
+    VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+    uint64_t total = 0;
+    for (uint32_t v : h) { total += v; }
+    if (total > 0xfffffff0ull) { cnt.release(); tmp.release(); delete ix; Error::set("cluster index: more than 2^32 k-mer occurrences in the sequence set"); return VSG_EINVAL; }
+    if ((rc = ix->b_post.reserve(sizeof(uint32_t) * (total + 64))) != VSG_OK) { cnt.release(); tmp.release(); delete ix; return rc; }
+  }
+  VSG_CUDA_OK(cudaMemcpyAsync(ix->b_cursor.p, ix->b_start.p, sizeof(uint32_t) * (hashsize + 1), cudaMemcpyDeviceToDevice, c->stream));
+  VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+  cnt.release(); tmp.release();
+  *out = ix;
+  return VSG_OK;
+}
+
+void cindex_destroy(CIndex * ix)
+{
+  if (ix == nullptr) { return; }
+  cudaSetDevice(ix->device);
+  for (DevBuf * b : {&ix->b_start, &ix->b_cursor, &ix->b_post, &ix->b_clen, &ix->b_shards, &ix->b_seqnos}) { b->release(); }
+  for (auto & b : ix->b_begin) { b.release(); }
+  delete ix;
+}
+
+// Dbindex::add_sequence for a batch of new targets (ascending sequence numbers); enqueued on c->stream
+int cindex_append(vsg_ctx * c, CIndex * ix, const uint32_t * seqnos, int n)
+{
+  if (n <= 0) { return VSG_OK; }
+  size_t const hashsize = static_cast<size_t>(1) << (2 * ix->k);
+  size_t const bitmap_bytes = std::max<size_t>(hashsize / 8, 4);
+  int rc;
+  int done = 0;
+  while (done < n) {
+    // never across a shard boundary in one launch: a shard's part of every list must be contiguous
+    int64_t const room = SHARD - (ix->ncent % SHARD);
+    int const m = static_cast<int>(std::min<int64_t>(n - done, room));
+    if ((rc = ix->b_seqnos.reserve(sizeof(uint32_t) * static_cast<size_t>(m) + 16)) != VSG_OK) { return rc; }
+    // the upload below reuses one small buffer: order it after the previous launch on the same stream
+    VSG_CUDA_OK(cudaMemcpyAsync(ix->b_seqnos.p, seqnos + done, sizeof(uint32_t) * static_cast<size_t>(m), cudaMemcpyHostToDevice, c->stream));
+    cindex_append_kernel<<<m, 128, bitmap_bytes, c->stream>>>(ix->set->d, static_cast<const uint32_t *>(ix->b_seqnos.p), m,
+                                                              static_cast<uint32_t>(ix->ncent), ix->k, ix->mask_lower,
+                                                              static_cast<uint32_t *>(ix->b_cursor.p), static_cast<uint32_t *>(ix->b_post.p),
+                                                              static_cast<int32_t *>(ix->b_clen.p));
+    count_launch();
+    VSG_CUDA_OK(cudaStreamSynchronize(c->stream));   // seqnos + done must stay valid; the launch is tiny
+    for (int i = 0; i < m; i++) { ix->h_seqno.push_back(seqnos[done + i]); }
+    ix->ncent += m;
+    done += m;
+    if (ix->ncent % SHARD == 0) {
+      ix->b_begin.emplace_back();
+      if ((rc = ix->b_begin.back().reserve(sizeof(uint32_t) * (hashsize + 1))) != VSG_OK) { return rc; }
+      VSG_CUDA_OK(cudaMemcpyAsync(ix->b_begin.back().p, ix->b_cursor.p, sizeof(uint32_t) * (hashsize + 1), cudaMemcpyDeviceToDevice, c->stream));
+    }
+  }
+  return VSG_OK;
+}
+
+const std::vector<uint32_t> & cindex_seqnos(const CIndex * ix) { return ix->h_seqno; }
+
+// search_topscores of queries [q0, q0+nq) of `queries` against the targets added so far; results as rank_enqueue,
+// candidate numbers are DENSE target numbers (CIndex::h_seqno maps them back)
+int cindex_rank_enqueue(vsg_ctx * c, CIndex * ix, const vsg_seqset * queries, int64_t q0, int64_t nq, int minwordmatches,
+                        int tophits, uint32_t ** d_seqno, uint32_t ** d_count, int32_t ** d_n, int32_t ** d_status)
+{
+  if (tophits < 1 || tophits > TOPHITS_MAX) { Error::set("cluster ranker: tophits must be in 1..1024"); return VSG_EINVAL; }
+  size_t const cells = static_cast<size_t>(nq) * tophits;
+  int rc;
+  if ((rc = c->rank_tmp.reserve(sizeof(uint32_t) * (2 * cells + nq + 4))) != VSG_OK) { return rc; }
+  *d_seqno = static_cast<uint32_t *>(c->rank_tmp.p);
+  *d_count = *d_seqno + cells;
+  *d_n = reinterpret_cast<int32_t *>(*d_count + cells);
+  *d_status = *d_n + nq;
+  VSG_CUDA_OK(cudaMemsetAsync(*d_status, 0, sizeof(int32_t), c->stream));
+  if (nq == 0) { return VSG_OK; }
+  int const nshards = static_cast<int>((ix->ncent + SHARD - 1) / SHARD);
+  if (nshards == 0) {   // nothing indexed yet: no candidates
+    VSG_CUDA_OK(cudaMemsetAsync(*d_n, 0, sizeof(int32_t) * nq, c->stream));
+    return VSG_OK;
+  }
+  std::vector<ShardDev> sh(static_cast<size_t>(nshards));
+  for (int s = 0; s < nshards; s++) {
+    ShardDev & sd = sh[static_cast<size_t>(s)];
+    sd.start = static_cast<const uint32_t *>(s == 0 ? ix->b_start.p : ix->b_begin[static_cast<size_t>(s) - 1].p);
+    sd.end = static_cast<const uint32_t *>(s + 1 < nshards || ix->ncent % SHARD == 0 ? ix->b_begin[static_cast<size_t>(s)].p : ix->b_cursor.p);
+    sd.post = nullptr; sd.post32 = static_cast<const uint32_t *>(ix->b_post.p);
+    sd.t0 = s * SHARD;
+    sd.nt = static_cast<int32_t>(std::min<int64_t>(SHARD, ix->ncent - static_cast<int64_t>(s) * SHARD));
+  }
+  if ((rc = ix->b_shards.reserve(sizeof(ShardDev) * sh.size())) != VSG_OK) { return rc; }
+  VSG_CUDA_OK(cudaMemcpyAsync(ix->b_shards.p, sh.data(), sizeof(ShardDev) * sh.size(), cudaMemcpyHostToDevice, c->stream));
+  VSG_CUDA_OK(cudaStreamSynchronize(c->stream));   // sh goes out of scope
+  VSG_CUDA_OK(cudaFuncSetAttribute(rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(RANK_SMEM)));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  int const grid = static_cast<int>(std::min<int64_t>(nq, static_cast<int64_t>(sms) * 2));
+  DevSeqs lens{nullptr, nullptr, static_cast<const int32_t *>(ix->b_clen.p), ix->ncent};   // target lengths by dense number
+  int maxlen = 0;
+  for (int64_t q = q0; q < q0 + nq; q++) { maxlen = std::max(maxlen, queries->h_len[static_cast<size_t>(q)]); }
+  uint32_t * d_scratch = nullptr;
+  size_t stride = 0;
+  int const bitmap_words = std::max(1, (1 << (2 * ix->k)) >> 5);
+  if (maxlen - ix->k + 1 > KMER_CAP) {
+    stride = static_cast<size_t>(bitmap_words) + static_cast<size_t>(maxlen) + 8;
+    if ((rc = c->rank_scratch.reserve(sizeof(uint32_t) * stride * static_cast<size_t>(grid))) != VSG_OK) { return rc; }
+    d_scratch = static_cast<uint32_t *>(c->rank_scratch.p);
+  }
+  rank_kernel<true><<<grid, RANK_THREADS, RANK_SMEM, c->stream>>>(
+      queries->d, q0, static_cast<int>(nq), lens, static_cast<const ShardDev *>(ix->b_shards.p), nshards, ix->k, ix->mask_lower,
+      minwordmatches, tophits, *d_seqno, *d_count, *d_n, *d_status, d_scratch, stride, bitmap_words);
+  count_launch();
+  return VSG_OK;
+}
+
+}  // namespace vsg

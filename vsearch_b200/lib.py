@@ -303,6 +303,26 @@ def allpairs(ctx: "Context", ss: SeqSetHandle, row0: int, nrows: int, opts: Sear
     return hits[: n.value], work
 
 
+class ClusterResult(C.Structure):
+    _fields_ = [("cluster", C.c_int32), ("centroid", C.c_int32), ("matches", C.c_int32), ("mismatches", C.c_int32),
+                ("gaps", C.c_int32), ("alignment_length", C.c_int32), ("nwscore", C.c_int32), ("strand", C.c_int32),
+                ("id", C.c_double)]
+
+
+def cluster_fast(ctx: "Context", ss: SeqSetHandle, opts: SearchOpts, round_size: int):
+    """vsg_cluster_fast -> (numpy structured array of per-sequence results, number of clusters, work[2])"""
+    dt = np.dtype([("cluster", np.int32), ("centroid", np.int32), ("matches", np.int32), ("mismatches", np.int32),
+                   ("gaps", np.int32), ("alignment_length", np.int32), ("nwscore", np.int32), ("strand", np.int32),
+                   ("id", np.float64)])
+    assert dt.itemsize == C.sizeof(ClusterResult)
+    res = np.zeros(ss.n, dtype=dt)
+    ncl = C.c_int64()
+    work = np.zeros(2, dtype=np.int64)
+    _check(load().vsg_cluster_fast(ctx.h, ss.h, C.byref(opts), C.c_int(round_size), res.ctypes.data_as(C.POINTER(ClusterResult)),
+                                   C.byref(ncl), _ptr(work, C.c_int64)), "vsg_cluster_fast")
+    return res, int(ncl.value), work
+
+
 class Group:
     """vsg_group: one process, several GPUs (database copied device to device, queries / rows sharded)"""
 
