@@ -324,6 +324,99 @@ def allpairs_workload(args, rank, world, local):
         dist.destroy_process_group()
 
 
+def cluster_workload(args, rank, world, local):
+    """configs[2] shape: --cluster_fast on 300-nt amplicon reads (1 % divergence, Zipf-ish root choice), --id 0.97.
+    One step = clustering a stated PREFIX of the read stream from scratch (the full 10 M reads are
+    hours on the CPU), round size = the host's core count on both arms (the reference's results depend on --threads).
+    cluster_fast is a sequential greedy: N GPUs run N independent replicas."""
+    from vsearch_b200 import synth
+    N = args.cluster_reads
+    cores = os.cpu_count() or 1
+    T = args.cluster_round if args.cluster_round > 0 else cores
+    rng = np.random.default_rng([3, rank if args.impl != "reference" else 0])
+    nroots = max(50, N // 200)
+    roots = synth.random_seqs(rng, nroots, 300)
+    w = 1.0 / np.arange(1, nroots + 1); w /= w.sum()
+    reads = synth.mutate_batch(rng, roots[rng.choice(nroots, size=N, p=w)], 0.01)
+    labels = [f"a{i:08d}" for i in range(N)]
+    order = np.lexsort((np.arange(N), -reads.lens.astype(np.int64)))     # Database::sortbylength (labels ascend with i)
+    cfg = {"workload": f"cluster_fast first {N} reads of the 300nt amplicon stream (configs[2] shape), id 0.97",
+           "reads_per_step": N, "round_size": T, "masking": "dust", "parallelism": f"{world} independent replica(s)"}
+    nsteps = args.warmup + args.steps
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        stock = os.path.join(ROOT, "oracle", "_ref", "vsearch")
+        if not os.path.exists(stock):
+            emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/vsearch not built"}))
+            return
+        fa = "/tmp/bench_cluster.fasta"
+        with open(fa, "wb") as f:
+            for i in range(N):
+                f.write(b">" + labels[i].encode() + b"\n" + reads.seq(i) + b"\n")
+        times = []
+        for step in range(max(1, min(nsteps, 2))):      # the CPU run is long: one warm-up, one timed
+            t0 = time.perf_counter()
+            p = subprocess.run([stock, "--cluster_fast", fa, "--id", "0.97", "--threads", str(T), "--uc", "/tmp/bench_cluster.uc", "--quiet"],
+                               capture_output=True, text=True)
+            times.append(time.perf_counter() - t0)
+            assert p.returncode == 0, p.stderr[-500:]
+        dt = times[-1]
+        ncl = sum(1 for l in open("/tmp/bench_cluster.uc") if l.startswith("S"))
+        emit(json.dumps({"impl": "reference", "metric": "cluster_fast_reads_per_s", "value": N / dt, "unit": "reads/s", "n_gpus": args.gpus,
+                          "steps": 1, "warmup": len(times) - 1, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "int16", "data": "synthetic", "config": cfg, "clusters": ncl, "host": host_info(),
+                          "cpu_baseline": {"value": N / dt, "unit": "reads/s", "cores": cores, "kind": "reference",
+                                           "sample": f"vsearch --cluster_fast --threads {T} on the same {N} reads, wall time of the CLI (FASTA read and uc write included)"},
+                          "e2e": {"value": N / dt, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    from vsearch_b200 import lib as vlib
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = vlib.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local))
+    sorted_host = pinned_seqset(synth.SeqSet([reads.seq(int(i)) for i in order]))
+    o = vlib.default_search_opts(); o.id = 0.97; o.mask_lower = 1; o.maxrejects = 8   # --cluster_fast default (cli.cc:4163-4172)
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    sampler = None; l0 = 0; work = np.zeros(2, dtype=np.int64); ncl = 0
+    for step in range(nsteps):
+        if step == args.warmup:
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            sampler = ClockSampler(local); sampler.start(); l0 = vlib.launch_count()
+            ev0.record(stream)
+        ss = ctx.seqset(sorted_host)     # upload + DUST + clustering + results: all inside the timed region
+        ss.dust()
+        res, ncl, w = vlib.cluster_fast(ctx, ss, o, T)
+        ss.close()
+        if step >= args.warmup:
+            work += w
+    ev1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.summary(); launches = vlib.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    if rank == 0:
+        rps = N * world * args.steps / (ms * 1e-3)
+        emit(json.dumps({"metric": "cluster_fast_reads_per_s", "value": rps, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "int16", "data": "synthetic", "config": cfg, "clusters": int(ncl),
+                          "aligned_pairs_per_step": int(work[0] // max(1, args.steps)), "gcups": float(work[1]) / (ms * 1e-3) / 1e9,
+                          "e2e": {"value": rps, "unit": "reads/s", "h2d_bytes_per_step": int(sorted_host.cat.nbytes + sorted_host.offs.nbytes + sorted_host.lens.nbytes),
+                                  "d2h_bytes_per_step": int(N * 40), "note": "value IS end to end: upload, DUST, clustering and the result table are inside the timed region"},
+                          "gpu_launches": int(launches), "clocks": clocks}))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 _RESULT_FD = None
 
 
@@ -356,10 +449,12 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the parity gate against the reference")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="queries of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="usearch", choices=["usearch", "c4", "allpairs"],
+    ap.add_argument("--workload", default="usearch", choices=["usearch", "c4", "allpairs", "cluster"],
                     help="usearch = configs[1] (default, the headline); c4 = configs[3] shape (1M x 1200 DB, 150-nt queries, "
                          "id 0.85); allpairs = configs[4] shape (dense N^2 DP)")
     ap.add_argument("--rows", type=int, default=32, help="allpairs: query rows per step per GPU")
+    ap.add_argument("--cluster-reads", type=int, default=200_000, help="cluster: reads per step (prefix of the configs[2] stream)")
+    ap.add_argument("--cluster-round", type=int, default=0, help="cluster: round size = the reference's --threads (0 = host cores)")
     ap.add_argument("--ref-rows", type=int, default=0,
                     help="allpairs: query rows per step of the reference arm (0 = one per host thread)")
     args = ap.parse_args()
@@ -372,6 +467,9 @@ def main():
 
     if args.workload == "allpairs":
         allpairs_workload(args, rank, world, local)
+        return
+    if args.workload == "cluster":
+        cluster_workload(args, rank, world, local)
         return
     set_workload(args.workload)
     if args.impl == "reference":

@@ -273,7 +273,8 @@ int vsg_allpairs(vsg_ctx * ctx, const vsg_seqset * set, int64_t row0, int64_t nr
  *      with `vsearch --cluster_fast --threads round_size`.  results[i] for sequence i: its cluster number
  *      (creation order of the centroids) and either centroid = -1 (it founded the cluster: an "S" record of
  *      --uc) or the sequence number of the centroid it matched plus that alignment's statistics and identity
- *      (an "H" record; the CIGAR is one vsg_align_pairs call away).  opts: id, iddef, maxaccepts, maxrejects,
+ *      (an "H" record; the CIGAR is one vsg_align_pairs call away).  NOTE the reference's default --maxrejects for
+ *      --cluster_fast is 8, not 32 (cli.cc:4163-4172): set opts->maxrejects accordingly.  opts: id, iddef, maxaccepts, maxrejects,
  *      wordlength, minwordmatches, mask_lower, the length / abundance / post-alignment filters (target_sizes
  *      and target_labels are per sequence of `set`); plus strand only.  work (optional, 2 x int64): pairs and DP
  *      cells handed to the aligner. ---- */

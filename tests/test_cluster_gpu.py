@@ -19,9 +19,11 @@ STOCK = os.path.join(ROOT, "oracle", "_ref", "vsearch")
 def _reads(n, nroots, seed, divs=(0.01, 0.01, 0.02, 0.035, 0.05)):
     rng = np.random.default_rng(seed)
     roots = synth.random_seqs(rng, nroots, 300)
+    w = 1.0 / np.arange(1, nroots + 1); w /= w.sum()      # Zipf-ish root choice: a few roots own most reads
+    pick = rng.choice(nroots, size=n, p=w)
     seqs = []
     for i in range(n):
-        r = roots[int(rng.integers(0, nroots))]
+        r = roots[int(pick[i])]
         m = synth.mutate(rng, r, float(divs[int(rng.integers(0, len(divs)))]))
         a = int(rng.integers(0, 6)); b = int(rng.integers(0, 6))
         s = m[a: m.shape[0] - b].tobytes()
@@ -44,7 +46,7 @@ def _uc_records(path):
 
 @pytest.mark.skipif(not os.path.exists(STOCK), reason="oracle/_ref/vsearch not built")
 @pytest.mark.parametrize("threads,n,nroots,ident", [(1, 1500, 40, 0.97), (2, 1500, 40, 0.97), (8, 4000, 120, 0.97),
-                                                     (64, 6000, 400, 0.97), (16, 3000, 60, 0.90)])
+                                                     (64, 6000, 400, 0.97), (16, 3000, 60, 0.90), (128, 30000, 150, 0.97)])
 def test_cluster_fast_equals_reference_cli(tmp_path, threads, n, nroots, ident):
     seqs = _reads(n, nroots, seed=100 + threads)
     labels = [f"a{i:07d}" for i in range(n)]
@@ -64,6 +66,7 @@ def test_cluster_fast_equals_reference_cli(tmp_path, threads, n, nroots, ident):
     ss = ctx.seqset(ss_host)
     ss.dust()                                   # --qmask dust, the default (dust_all before clustering)
     o = vlib.default_search_opts(); o.id = ident; o.mask_lower = 1
+    o.maxrejects = 8                            # the reference's default for --cluster_fast (cli.cc:4163-4172); 32 elsewhere
     res, ncl, work = vlib.cluster_fast(ctx, ss, o, threads)
     assert ncl == sum(1 for v in want.values() if v[0] == "S")
     hq = [k for k in range(n) if res["centroid"][k] >= 0]

@@ -35,12 +35,24 @@ def make_world(rng, nq, nt):
     return [draw() for _ in range(nq)], [draw() for _ in range(nt)]
 
 
+@pytest.fixture(params=["checkpoints", "direction-bits"])
+def path(request):
+    """both aligner paths: checkpoint kernels (threshold 0) and direction-bit kernels (threshold above any batch)"""
+    old = os.environ.get("VSG_CKPT_MIN_PAIRS")
+    os.environ["VSG_CKPT_MIN_PAIRS"] = "0" if request.param == "checkpoints" else "1000000000"
+    yield request.param
+    if old is None:
+        os.environ.pop("VSG_CKPT_MIN_PAIRS", None)
+    else:
+        os.environ["VSG_CKPT_MIN_PAIRS"] = old
+
+
 @pytest.mark.parametrize("seed,pen,budget", [
     (101, None, None),
     (102, [1, -2, 3, 3, 10, 10, 3, 3, 1, 1, 1, 1, 1, 1], "2"),
     (103, [5, -4, 0, 0, 12, 16, 0, 0, 0, 0, 3, 2, 0, 0], None),
 ])
-def test_random_pairs(seed, pen, budget):
+def test_random_pairs(seed, pen, budget, path):
     rng = np.random.default_rng(seed)
     if budget:
         os.environ["VSG_DIR_BUDGET_MB"] = budget

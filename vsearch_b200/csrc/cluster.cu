@@ -17,6 +17,9 @@
 #include "hit_logic.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -42,12 +45,16 @@ struct CQuery {   // one searchinfo_s of the round (plus strand)
   std::vector<Hit> hits;
   int accepts = 0, rejects = 0, finalized = 0, delayed = 0;
   bool done = false, waiting = false;
-  std::vector<uint32_t> kmers;     // distinct unmasked k-mers, sorted (filled when an extra hit needs them)
+  std::vector<uint32_t> kmers;     // distinct unmasked k-mers (filled when an extra hit needs them)
   bool have_kmers = false;
+  std::vector<uint64_t> bitmap;    // the same set as a 4^k-bit map (built when the query becomes a candidate centroid)
+  bool have_bitmap = false;
 };
 
-// unique_count (core/unique.cpp:155-240): the distinct k-mers of the windows that hold no masked symbol
-void distinct_kmers(const uint8_t * sym, int len, int k, int mask_lower, std::vector<uint32_t> & out)
+// unique_count (core/unique.cpp:155-240): the distinct k-mers of the windows that hold no masked symbol.
+// `stamp` (4^k words) de-duplicates without being cleared: a k-mer is new iff its stamp differs from `tag`.
+void distinct_kmers(const uint8_t * sym, int len, int k, int mask_lower, std::vector<uint32_t> & stamp, uint32_t tag,
+                    std::vector<uint32_t> & out)
 {
   out.clear();
   uint32_t const mask = k < 16 ? ((1u << (2 * k)) - 1u) : 0xffffffffu;
@@ -59,19 +66,15 @@ void distinct_kmers(const uint8_t * sym, int len, int k, int mask_lower, std::ve
     bool const bad = !single || (mask_lower && (s & 16));
     v = ((v << 2) | (c == 2 ? 1u : c == 4 ? 2u : c == 8 ? 3u : 0u)) & mask;
     good = bad ? 0 : good + 1;
-    if (good >= k) { out.push_back(v); }
+    if (good >= k && stamp[v] != tag) { stamp[v] = tag; out.push_back(v); }
   }
-  std::sort(out.begin(), out.end());
-  out.erase(std::unique(out.begin(), out.end()), out.end());
 }
 
-unsigned shared_count(const std::vector<uint32_t> & a, const std::vector<uint32_t> & b)
+// unique_count_shared (core/unique.cpp): how many of a's distinct k-mers are in the set `bm`
+unsigned shared_count(const std::vector<uint32_t> & a, const std::vector<uint64_t> & bm)
 {
   unsigned n = 0;
-  size_t i = 0, j = 0;
-  while (i < a.size() && j < b.size()) {
-    if (a[i] < b[j]) { i++; } else if (a[i] > b[j]) { j++; } else { n++; i++; j++; }
-  }
+  for (uint32_t v : a) { n += static_cast<unsigned>((bm[v >> 6] >> (v & 63)) & 1u); }
   return n;
 }
 
@@ -128,6 +131,8 @@ extern "C" int vsg_cluster_fast(vsg_ctx * c, const vsg_seqset * set, const vsg_s
   std::vector<uint8_t> round_sym;
   std::vector<uint32_t> new_centroids;
   const std::vector<uint32_t> & dense_to_seqno = cindex_seqnos(ix);
+  std::vector<uint32_t> stamp(static_cast<size_t>(1) << (2 * k), 0u);
+  uint32_t stamp_tag = 0;
 
   // the statistics search16 returned for one (query, target) -> struct hit (searchcore.cpp:842-857 / cluster.cpp:786-809)
   auto fill_hit = [&](Hit & h, int qlen, int16_t sc, uint16_t al, uint16_t ma, uint16_t mi, uint16_t ga, const int32_t * tr,
@@ -160,8 +165,13 @@ extern "C" int vsg_cluster_fast(vsg_ctx * c, const vsg_seqset * set, const vsg_s
     finish_hit(h, trims4, opts->iddef);
   };
 
+  static const bool trace = std::getenv("VSG_TRACE") != nullptr;
+  auto now = []() { return std::chrono::steady_clock::now(); };
+  auto ms_since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
+  double t_rank = 0, t_groups = 0, t_spec = 0, t_serial = 0, t_append = 0;
   for (int64_t round0 = 0; round0 < seqcount; round0 += round_size) {
     int const nqr = static_cast<int>(std::min<int64_t>(round_size, seqcount - round0));
+    auto tp = now();
     // ---- 1a. candidate ranking of the whole round against the centroids indexed so far ----
     size_t const cells = static_cast<size_t>(nqr) * tophits;
     h_seqno.resize(cells); h_count.resize(cells); h_n.resize(static_cast<size_t>(nqr));
@@ -176,6 +186,7 @@ extern "C" int vsg_cluster_fast(vsg_ctx * c, const vsg_seqset * set, const vsg_s
       VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
       if (status != 0) { Error::set("vsg_cluster_fast: a sequence is longer than the device ranker supports (65 534 + wordlength nt)"); return VSG_EINVAL; }
     }
+    t_rank += ms_since(tp); tp = now();
     for (int i = 0; i < nqr; i++) {
       CQuery & S = rq[static_cast<size_t>(i)];
       S.seqno = static_cast<int>(round0 + i);
@@ -185,7 +196,7 @@ extern "C" int vsg_cluster_fast(vsg_ctx * c, const vsg_seqset * set, const vsg_s
       S.cc = h_count.data() + static_cast<size_t>(i) * tophits;
       S.hits.clear();
       S.accepts = S.rejects = S.finalized = S.delayed = 0;
-      S.done = false; S.waiting = false; S.have_kmers = false;
+      S.done = false; S.waiting = false; S.have_kmers = false; S.have_bitmap = false;
     }
     // ---- 1b. search_onequery for every query of the round, in lock step (searchcore.cpp:915-954) ----
     bool any = true;
@@ -247,33 +258,94 @@ extern "C" int vsg_cluster_fast(vsg_ctx * c, const vsg_seqset * set, const vsg_s
         S.finalized = static_cast<int>(S.hits.size()); S.delayed = 0;
       }
     }
+    t_groups += ms_since(tp); tp = now();
     // ---- 2. the serial pass (cluster.cpp:946-1025) ----
     new_centroids.clear();
     bool have_sym = false;
-    int64_t const sym0 = 0;   // round_sym holds the symbols of sequences round0 .. round0+nqr-1, each at its own offset
     std::vector<int64_t> sym_off;
     auto need_kmers = [&](int i) -> int {
       CQuery & S = rq[static_cast<size_t>(i)];
       if (S.have_kmers) { return VSG_OK; }
       if (!have_sym) {
-        // one download of the round's symbols (consecutive sequences need not be contiguous: copy each)
+        // one download of the round's symbols (one copy when the sequences lie back to back, as they do for a packed set)
         sym_off.assign(static_cast<size_t>(nqr) + 1, 0);
-        for (int z = 0; z < nqr; z++) { sym_off[static_cast<size_t>(z) + 1] = sym_off[static_cast<size_t>(z)] + set->h_len[static_cast<size_t>(round0 + z)]; }
-        round_sym.resize(static_cast<size_t>(sym_off[static_cast<size_t>(nqr)]) + 1);
-        std::vector<int64_t> h_off(static_cast<size_t>(nqr));
-        VSG_CUDA_OK(cudaMemcpyAsync(h_off.data(), set->d.off + round0, sizeof(int64_t) * nqr, cudaMemcpyDeviceToHost, c->stream));
-        VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+        bool contiguous = true;
         for (int z = 0; z < nqr; z++) {
-          int const l = set->h_len[static_cast<size_t>(round0 + z)];
-          if (l > 0) { VSG_CUDA_OK(cudaMemcpyAsync(round_sym.data() + sym_off[static_cast<size_t>(z)], set->d.sym + h_off[static_cast<size_t>(z)], static_cast<size_t>(l), cudaMemcpyDeviceToHost, c->stream)); }
+          size_t const sq = static_cast<size_t>(round0 + z);
+          sym_off[static_cast<size_t>(z) + 1] = sym_off[static_cast<size_t>(z)] + set->h_len[sq];
+          if (z + 1 < nqr && set->h_off[sq + 1] != set->h_off[sq] + set->h_len[sq]) { contiguous = false; }
+        }
+        round_sym.resize(static_cast<size_t>(sym_off[static_cast<size_t>(nqr)]) + 1);
+        if (contiguous) {
+          if (sym_off[static_cast<size_t>(nqr)] > 0) {
+            VSG_CUDA_OK(cudaMemcpyAsync(round_sym.data(), set->d.sym + set->h_off[static_cast<size_t>(round0)], static_cast<size_t>(sym_off[static_cast<size_t>(nqr)]), cudaMemcpyDeviceToHost, c->stream));
+          }
+        } else {
+          for (int z = 0; z < nqr; z++) {
+            int const l = set->h_len[static_cast<size_t>(round0 + z)];
+            if (l > 0) { VSG_CUDA_OK(cudaMemcpyAsync(round_sym.data() + sym_off[static_cast<size_t>(z)], set->d.sym + set->h_off[static_cast<size_t>(round0 + z)], static_cast<size_t>(l), cudaMemcpyDeviceToHost, c->stream)); }
+          }
         }
         VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
         have_sym = true;
       }
-      distinct_kmers(round_sym.data() + sym_off[static_cast<size_t>(i)] + sym0, S.qlen, k, opts->mask_lower, S.kmers);
+      if (++stamp_tag == 0) { std::fill(stamp.begin(), stamp.end(), 0u); stamp_tag = 1; }
+      distinct_kmers(round_sym.data() + sym_off[static_cast<size_t>(i)], S.qlen, k, opts->mask_lower, stamp, stamp_tag, S.kmers);
       S.have_kmers = true;
       return VSG_OK;
     };
+    auto need_bitmap = [&](int j) -> int {
+      CQuery & C = rq[static_cast<size_t>(j)];
+      if (C.have_bitmap) { return VSG_OK; }
+      int const r = need_kmers(j);
+      if (r != VSG_OK) { return r; }
+      C.bitmap.assign(((static_cast<size_t>(1) << (2 * k)) + 63) / 64, 0);
+      for (uint32_t v : C.kmers) { C.bitmap[v >> 6] |= static_cast<uint64_t>(1) << (v & 63); }
+      C.have_bitmap = true;
+      return VSG_OK;
+    };
+    // Speculative batch for the serial pass: a query without an accepted hit MAY found a cluster; every later
+    // query of the round that shares enough k-mers with it MAY then have to be aligned against it
+    // (evaluate_extra_hits aligns such pairs one at a time, cluster.cpp:741-752).  All those pairs go to the
+    // device in one call; the serial pass below takes its alignments from here and falls back to a single-pair
+    // call for anything not foreseen.  Decisions are unaffected; only alignments nobody asks for are extra work.
+    struct Spec { int16_t sc; uint16_t al, ma, mi, ga; int32_t tr[4]; };
+    std::vector<std::pair<uint64_t, Spec>> spec;   // key = (i << 32) | j, sorted
+    {
+      std::vector<int> maybe;
+      for (int i = 0; i < nqr; i++) { if (rq[static_cast<size_t>(i)].accepts == 0) { maybe.push_back(i); } }
+      pq.clear(); pt.clear();
+      std::vector<uint64_t> keys;
+      if (!maybe.empty() && nqr > 1) {
+        for (int i = 1; i < nqr; i++) {
+          for (int j : maybe) {
+            if (j >= i) { break; }
+            if ((rc = need_kmers(i)) != VSG_OK || (rc = need_bitmap(j)) != VSG_OK) { return rc; }
+            CQuery & S = rq[static_cast<size_t>(i)];
+            CQuery & C = rq[static_cast<size_t>(j)];
+            unsigned const shared = shared_count(S.kmers, C.bitmap);
+            if (!(shared >= static_cast<unsigned>(minwordmatches) || shared >= S.kmers.size())) { continue; }
+            if (!unaligned_ok(S.seqno, S.qlen, C.seqno)) { continue; }
+            pq.push_back(static_cast<uint32_t>(S.seqno)); pt.push_back(static_cast<uint32_t>(C.seqno));
+            keys.push_back((static_cast<uint64_t>(i) << 32) | static_cast<uint64_t>(j));
+          }
+        }
+      }
+      size_t const np = pq.size();
+      if (np > 0) {
+        a_score.resize(np); a_al.resize(np); a_ma.resize(np); a_mi.resize(np); a_ga.resize(np); a_tr.resize(np * 4);
+        rc = vsg_align_pairs(c, set, set, static_cast<int64_t>(np), pq.data(), pt.data(), a_score.data(), a_al.data(), a_ma.data(),
+                             a_mi.data(), a_ga.data(), a_tr.data(), nullptr, 0, nullptr);
+        if (rc != VSG_OK) { return rc; }
+        spec.reserve(np);
+        for (size_t p = 0; p < np; p++) {
+          Spec sp1{a_score[p], a_al[p], a_ma[p], a_mi[p], a_ga[p], {a_tr[4 * p], a_tr[4 * p + 1], a_tr[4 * p + 2], a_tr[4 * p + 3]}};
+          spec.emplace_back(keys[p], sp1);
+        }
+        std::sort(spec.begin(), spec.end(), [](const std::pair<uint64_t, Spec> & a, const std::pair<uint64_t, Spec> & b) { return a.first < b.first; });
+      }
+    }
+    t_spec += ms_since(tp); tp = now();
     std::vector<int> extra_list;
     for (int i = 0; i < nqr; i++) {
       CQuery & S = rq[static_cast<size_t>(i)];
@@ -283,8 +355,8 @@ extern "C" int vsg_cluster_fast(vsg_ctx * c, const vsg_seqset * set, const vsg_s
         if ((rc = need_kmers(i)) != VSG_OK) { return rc; }
         for (int j : extra_list) {
           CQuery & C = rq[static_cast<size_t>(j)];
-          if ((rc = need_kmers(j)) != VSG_OK) { return rc; }
-          unsigned const shared = shared_count(S.kmers, C.kmers);
+          if ((rc = need_bitmap(j)) != VSG_OK) { return rc; }
+          unsigned const shared = shared_count(S.kmers, C.bitmap);
           // search_enough_kmers (searchcore.cpp:252-257)
           if (!(shared >= static_cast<unsigned>(minwordmatches) || shared >= S.kmers.size())) { continue; }
           unsigned const length = static_cast<unsigned>(C.qlen);
@@ -311,8 +383,21 @@ extern "C" int vsg_cluster_fast(vsg_ctx * c, const vsg_seqset * set, const vsg_s
             if (unaligned_ok(S.seqno, S.qlen, h.target)) {
               uint32_t const q1 = static_cast<uint32_t>(S.seqno), t1 = static_cast<uint32_t>(h.target);
               int16_t sc; uint16_t al, ma, mi, ga; int32_t tr[4];
-              rc = vsg_align_pairs(c, set, set, 1, &q1, &t1, &sc, &al, &ma, &mi, &ga, tr, nullptr, 0, nullptr);   // "only using 1 sequence" (cluster.cpp:741-752)
-              if (rc != VSG_OK) { return rc; }
+              // "only using 1 sequence" (cluster.cpp:741-752): from the speculative batch if it is a centroid of this round
+              bool found = false;
+              if (h.target >= round0) {
+                uint64_t const key = (static_cast<uint64_t>(i) << 32) | static_cast<uint64_t>(h.target - round0);
+                auto const it = std::lower_bound(spec.begin(), spec.end(), key, [](const std::pair<uint64_t, Spec> & a, uint64_t kk) { return a.first < kk; });
+                if (it != spec.end() && it->first == key) {
+                  sc = it->second.sc; al = it->second.al; ma = it->second.ma; mi = it->second.mi; ga = it->second.ga;
+                  for (int z = 0; z < 4; z++) { tr[z] = it->second.tr[z]; }
+                  found = true;
+                }
+              }
+              if (!found) {
+                rc = vsg_align_pairs(c, set, set, 1, &q1, &t1, &sc, &al, &ma, &mi, &ga, tr, nullptr, 0, nullptr);
+                if (rc != VSG_OK) { return rc; }
+              }
               total_pairs++; total_cells += static_cast<int64_t>(S.qlen) * set->h_len[static_cast<size_t>(h.target)];
               int rcode = VSG_OK;
               fill_hit(h, S.qlen, sc, al, ma, mi, ga, tr, S.seqno, rcode);
@@ -351,10 +436,17 @@ extern "C" int vsg_cluster_fast(vsg_ctx * c, const vsg_seqset * set, const vsg_s
         new_centroids.push_back(static_cast<uint32_t>(S.seqno));
       }
     }
+    t_serial += ms_since(tp); tp = now();
     // Dbindex::add_sequence for the round's new centroids (they were visible to the rest of the round as extras)
     if (!new_centroids.empty()) {
       if ((rc = cindex_append(c, ix, new_centroids.data(), static_cast<int>(new_centroids.size()))) != VSG_OK) { return rc; }
     }
+    t_append += ms_since(tp);
+  }
+  if (trace) {
+    std::fprintf(stderr, "[vsg trace] cluster_fast %lld sequences, round %d: rank %.0f ms, candidate groups %.0f ms, speculative extras %.0f ms, "
+                 "serial pass %.0f ms, index append %.0f ms; %lld pairs\n", static_cast<long long>(seqcount), round_size, t_rank, t_groups,
+                 t_spec, t_serial, t_append, static_cast<long long>(total_pairs));
   }
   if (nclusters != nullptr) { *nclusters = clusters; }
   if (work != nullptr) { work[0] = total_pairs; work[1] = total_cells; }

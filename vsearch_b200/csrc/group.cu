@@ -43,6 +43,7 @@ int clone_seqset(vsg_ctx * c, const vsg_seqset * src, vsg_seqset ** out)
   s->device = c->device;
   s->h_len = src->h_len;
   s->h_nonacgt = src->h_nonacgt;
+  s->h_off = src->h_off;
   s->total = src->total;
   int64_t const n = src->d.n;
   int rc;

@@ -849,15 +849,17 @@ int cindex_append(vsg_ctx * c, CIndex * ix, const uint32_t * seqnos, int n)
     // never across a shard boundary in one launch: a shard's part of every list must be contiguous
     int64_t const room = SHARD - (ix->ncent % SHARD);
     int const m = static_cast<int>(std::min<int64_t>(n - done, room));
-    if ((rc = ix->b_seqnos.reserve(sizeof(uint32_t) * static_cast<size_t>(m) + 16)) != VSG_OK) { return rc; }
+    if (sizeof(uint32_t) * static_cast<size_t>(m) + 16 > ix->b_seqnos.cap) {
+      VSG_CUDA_OK(cudaStreamSynchronize(c->stream));   // the buffer is about to be replaced: let earlier launches finish with it
+      if ((rc = ix->b_seqnos.reserve(sizeof(uint32_t) * static_cast<size_t>(std::max(m, 4096)) + 16)) != VSG_OK) { return rc; }
+    }
     // the upload below reuses one small buffer: order it after the previous launch on the same stream
     VSG_CUDA_OK(cudaMemcpyAsync(ix->b_seqnos.p, seqnos + done, sizeof(uint32_t) * static_cast<size_t>(m), cudaMemcpyHostToDevice, c->stream));
     cindex_append_kernel<<<m, 128, bitmap_bytes, c->stream>>>(ix->set->d, static_cast<const uint32_t *>(ix->b_seqnos.p), m,
                                                               static_cast<uint32_t>(ix->ncent), ix->k, ix->mask_lower,
                                                               static_cast<uint32_t *>(ix->b_cursor.p), static_cast<uint32_t *>(ix->b_post.p),
                                                               static_cast<int32_t *>(ix->b_clen.p));
-    count_launch();
-    VSG_CUDA_OK(cudaStreamSynchronize(c->stream));   // seqnos + done must stay valid; the launch is tiny
+    count_launch();   // (the copy above is from pageable memory: staged before cudaMemcpyAsync returns)
     for (int i = 0; i < m; i++) { ix->h_seqno.push_back(seqnos[done + i]); }
     ix->ncent += m;
     done += m;
@@ -902,8 +904,8 @@ int cindex_rank_enqueue(vsg_ctx * c, CIndex * ix, const vsg_seqset * queries, in
     sd.nt = static_cast<int32_t>(std::min<int64_t>(SHARD, ix->ncent - static_cast<int64_t>(s) * SHARD));
   }
   if ((rc = ix->b_shards.reserve(sizeof(ShardDev) * sh.size())) != VSG_OK) { return rc; }
+  // pageable source: staged before the call returns, so `sh` may go out of scope
   VSG_CUDA_OK(cudaMemcpyAsync(ix->b_shards.p, sh.data(), sizeof(ShardDev) * sh.size(), cudaMemcpyHostToDevice, c->stream));
-  VSG_CUDA_OK(cudaStreamSynchronize(c->stream));   // sh goes out of scope
   VSG_CUDA_OK(cudaFuncSetAttribute(rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(RANK_SMEM)));
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);

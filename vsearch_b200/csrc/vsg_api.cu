@@ -317,6 +317,7 @@ extern "C" int vsg_seqset_create(vsg_ctx * c, const char * cat, const int64_t * 
     total = std::max<int64_t>(total, h_off[i] + s->h_len[i]);
   }
   s->total = total;
+  s->h_off = h_off;
   int rc;
   if ((rc = s->b_sym.reserve(static_cast<size_t>(total) + 64)) != VSG_OK ||
       (rc = s->b_off.reserve(sizeof(int64_t) * static_cast<size_t>(n) + 8)) != VSG_OK ||
@@ -384,6 +385,7 @@ int seqset_revcomp(vsg_ctx * c, const vsg_seqset * src, int64_t q0, int64_t n, v
   int64_t total = 0;
   for (int64_t i = 0; i < n; i++) { h_off[static_cast<size_t>(i)] = total; total += s->h_len[static_cast<size_t>(i)]; }
   s->total = total;
+  s->h_off = h_off;
   int rc;
   if ((rc = s->b_sym.reserve(static_cast<size_t>(total) + 64)) != VSG_OK ||
       (rc = s->b_off.reserve(sizeof(int64_t) * static_cast<size_t>(n) + 8)) != VSG_OK ||
@@ -565,6 +567,13 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
   ScoreParams const & sp = c->sp;
   FastBound const fbound = fast_bound_of(sp);
   FastBound const fbound2 = fast_bound_of(c->sp2);
+  // Small calls are latency-bound (the cluster driver's rounds, the tail rounds of a search): one thread
+  // regenerating ~40 tiles takes several hundred microseconds whatever the batch size, while walking stored
+  // direction bits takes tens.  Below VSG_CKPT_MIN_PAIRS pairs (default 2048) the direction-bit kernels are used;
+  // both paths are bit-identical (tests/test_stress_gpu.py runs either).
+  const char * const ckpt_min_env = std::getenv("VSG_CKPT_MIN_PAIRS");   // read per call: tests switch it
+  int64_t const ckpt_min_pairs = ckpt_min_env != nullptr ? std::atoll(ckpt_min_env) : 2048LL;
+  bool const use_ckpt = c->ckpt_enabled && npairs >= ckpt_min_pairs;
   std::vector<FastTask> all_fast;
   std::vector<ExactTask> all_exact;
   std::vector<PairDesc> all_pairs;  // CIGAR mode only
@@ -685,7 +694,7 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
         int const dmax = std::max(a.d, b.d);
         // single-strip tasks go through the checkpoint kernel (no direction bits; align_ckpt.cuh) when its
         // shifted scoring stays inside the exact range too
-        bool const ck = (ns == 1) && c->ckpt_enabled && fast_path_ok(fbound2, 32 * R, dmax);
+        bool const ck = (ns == 1) && use_ckpt && fast_path_ok(fbound2, 32 * R, dmax);
         uint64_t const dirb = ck ? ck_row_elems(dmax) * sizeof(uint2) : static_cast<uint64_t>(ns) * fast_strip_bytes(dmax, R);
         uint64_t const auxe = ck ? ck_col_elems(dmax, R) : (ns > 1 ? static_cast<uint64_t>(dmax) : 0);
         if (!cb.empty() && cb.dir_bytes + dirb + (cb.bnd_elems + auxe) * sizeof(uint2) > c->dir_budget) { close_chunk(); }

@@ -105,6 +105,7 @@ void count_launch(int n = 1);
 struct vsg_seqset {
   vsg::DevSeqs d{};
   std::vector<int32_t> h_len;       // host copy of lengths
+  std::vector<int64_t> h_off;       // host copy of offsets
   std::vector<uint8_t> h_nonacgt;   // 1 if the sequence holds a symbol outside ACGTU
   vsg::DevBuf b_sym, b_off, b_len;
   int device = 0;
