@@ -263,8 +263,7 @@ def allpairs_workload(args, rank, world, local):
     import torch.distributed as dist
     from vsearch_b200 import lib as vlib
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pg_init(world, local)
     ctx = vlib.Context(local)
     stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local))
     if world > 1:   # rank 0's packed reads go to every GPU over NCCL
@@ -320,8 +319,7 @@ def allpairs_workload(args, rank, world, local):
                                        "peak": 2.0 * peak_ops / 15.0 / 1e9, "unit": "GCUPS", "frac": g / (2.0 * peak_ops / 15.0 / 1e9),
                                        "note": "frac uses whole-step throughput (forward + traceback + host) against the forward-kernel peak"}}))
     ss.close(); ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    pg_done(world)
 
 
 def cluster_workload(args, rank, world, local):
@@ -373,9 +371,8 @@ def cluster_workload(args, rank, world, local):
     import torch
     from vsearch_b200 import lib as vlib
     torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import torch.distributed as dist
+    pg_init(world, local)
     ctx = vlib.Context(local)
     stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local))
     sorted_host = pinned_seqset(synth.SeqSet([reads.seq(int(i)) for i in order]))
@@ -413,15 +410,37 @@ def cluster_workload(args, rank, world, local):
                                   "d2h_bytes_per_step": int(N * 40), "note": "value IS end to end: upload, DUST, clustering and the result table are inside the timed region"},
                           "gpu_launches": int(launches), "clocks": clocks}))
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    pg_done(world)
 
 
 _RESULT_FD = None
+_SINK = None      # when a list: emit() collects result lines (legs of the default run) instead of printing them
+
+
+def pg_init(world, local):
+    """NCCL process group, once per process (the legs of the default run share it)"""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+
+def pg_done(world):
+    if world <= 1 or _SINK is not None:
+        return
+    import torch.distributed as dist
+    if dist.is_initialized():
+        dist.destroy_process_group()
 
 
 def emit(text):
     """the result line: the only thing this program writes to its original stdout"""
+    if _SINK is not None:
+        _SINK.append(json.loads(text))
+        return
     os.write(_RESULT_FD if _RESULT_FD is not None else 1, (text + "\n").encode())
 
 
@@ -457,6 +476,8 @@ def main():
     ap.add_argument("--cluster-round", type=int, default=0, help="cluster: round size = the reference's --threads (0 = host cores)")
     ap.add_argument("--ref-rows", type=int, default=0,
                     help="allpairs: query rows per step of the reference arm (0 = one per host thread)")
+    ap.add_argument("--no-legs", action="store_true",
+                    help="default run only: skip the short configs[2] / configs[3] / configs[4] legs appended to the headline line")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -475,7 +496,52 @@ def main():
     if args.impl == "reference":
         reference_arm(args, rank)
         return
+    if args.workload == "usearch" and not args.no_legs:
+        # the default run: headline (configs[1]) plus short legs of the other configurations, ONE JSON line
+        global _SINK
+        _SINK = []
+        rc = 0
+        try:
+            usearch_workload(args, rank, world, local)
+        except SystemExit as e:
+            rc = e.code if isinstance(e.code, int) else 1
+        line = _SINK[0] if _SINK else None
+        legs = {}
+        import copy
+        for name, fn, over in (
+                ("configs3_c4", usearch_workload, dict(workload="c4", steps=2, warmup=3, batch=32768, no_cpu_baseline=True, no_parity=True)),
+                ("configs4_allpairs", allpairs_workload, dict(workload="allpairs", steps=2, warmup=3, rows=24)),
+                ("configs2_cluster", cluster_workload, dict(workload="cluster", steps=1, warmup=3, cluster_reads=100_000))):
+            a2 = copy.copy(args)
+            for k_, v_ in over.items():
+                setattr(a2, k_, v_)
+            a2.leg = True
+            del _SINK[:]
+            if a2.workload == "c4":
+                set_workload("c4")
+            try:
+                fn(a2, rank, world, local)
+                if _SINK:
+                    d = _SINK[0]
+                    legs[name] = {k_: d[k_] for k_ in ("metric", "value", "unit", "ms_per_step", "steps", "config", "e2e", "gpu_launches",
+                                                         "queries_per_s", "pairs_per_s", "clusters", "gcups", "hits_per_step") if k_ in d}
+            except BaseException as e:   # a leg must never take the headline down
+                legs[name] = {"error": repr(e)[:300]}
+            set_workload("usearch")
+        _SINK = None
+        pg_done(world)
+        if rank == 0 and line is not None:
+            line["legs"] = legs
+            emit(json.dumps(line))
+        if rc:
+            raise SystemExit(rc)
+        return
+    usearch_workload(args, rank, world, local)
 
+
+def usearch_workload(args, rank, world, local):
+    """configs[1] (headline) / configs[3] shape: --usearch_global through vsg_search_batch"""
+    leg = getattr(args, "leg", False)
     import torch
     import torch.distributed as dist
     from vsearch_b200 import lib as vlib, synth
@@ -484,9 +550,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference "
                          "for the reference's CPU arm)")
     torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pg_init(world, local)
 
     ctx = vlib.Context(local)
     stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local))
@@ -582,6 +646,19 @@ def main():
             work_tot = w.cpu().numpy()
         return ms, work_tot, launches, prof, clocks, hits
 
+    if leg:     # a leg of the default run: the end-to-end number only
+        ms_e2e, work_e2e, launches, prof, clocks, hits = run_steps(e2e=True)
+        if rank == 0:
+            emit(json.dumps({"metric": "usearch_global_gcups", "value": float(work_e2e[1]) / (ms_e2e * 1e-3) / 1e9, "unit": "GCUPS",
+                              "steps": args.steps, "ms_per_step": ms_e2e / args.steps,
+                              "config": {"workload": WL_NAME, "queries_per_step_per_gpu": args.batch, "index_build_ms_per_gpu": round(index_build_ms, 1),
+                                         "masking": args.masking},
+                              "queries_per_s": args.batch * world * args.steps / (ms_e2e * 1e-3), "pairs_per_s": float(work_e2e[0]) / (ms_e2e * 1e-3),
+                              "gpu_launches": int(launches),
+                              "e2e": {"value": float(work_e2e[1]) / (ms_e2e * 1e-3) / 1e9, "unit": "GCUPS",
+                                      "note": "value IS end to end: query upload and hit table download inside the timed region"}}))
+        ix.close(); db.close(); ctx.close()
+        return
     ms_dev, work_dev, launches, prof, clocks, hits = run_steps(e2e=False)
     ms_e2e, work_e2e, _, _, _, _ = run_steps(e2e=True)
     # optional mode, reported separately and NOT the headline: candidates are aligned only when the
@@ -737,8 +814,7 @@ def main():
         line.update(parity)
         emit(json.dumps(line))
     ix.close(); db.close(); ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    pg_done(world)
     if parity["parity_mismatches"]:
         raise SystemExit(3)
 

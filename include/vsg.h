@@ -79,8 +79,10 @@ int vsg_ctx_set_fallback(vsg_ctx * ctx, vsg_fallback_fn fn, void * user);
 /* ---- sequences: replaces Database::add / getsequence / getsequencelen
  *      (core/db.hpp:137-201, core/db.cpp:170-226).  ASCII, one byte per nucleotide, any case,
  *      IUPAC allowed; offsets index into `cat`. `host` selects where cat/off/len live
- *      (1 = host memory, copied; 0 = device memory of ctx's device, adopted by reference and
- *      required to outlive the seqset — used after an NCCL broadcast). ---- */
+ *      (1 = host memory; 0 = device memory of ctx's device, e.g. after an NCCL broadcast).  Either way the
+ *      data is COPIED (encoded into the library's own symbol buffer): the caller may free its arrays when
+ *      the call returns.  A seqset / index belongs to the device of the context that made it; passing it to
+ *      a context of another device is an error (VSG_EINVAL). ---- */
 int vsg_seqset_create(vsg_ctx * ctx, const char * cat, const int64_t * off, const int32_t * len,
                       int64_t n, int host, vsg_seqset ** out);
 void vsg_seqset_destroy(vsg_seqset * s);

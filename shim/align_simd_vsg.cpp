@@ -18,6 +18,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -33,16 +34,18 @@ namespace {
 
 // The reference's Database is shared read-only by all worker threads (LIBRARY_API.md:962-999): keep
 // one device-resident copy per Database object, re-uploaded if the object is seen to have changed
-// (cluster_* appends centroids between rounds).
+// (cluster_* appends centroids between rounds).  Mirrors are reference counted: a search16 call keeps
+// the one it started with alive even if another thread replaces it meanwhile.
 struct DbMirror {
   Database const * db = nullptr;
   uint64_t count = 0;
   char const * first = nullptr;
   uint64_t nucleotides = 0;
   vsg_seqset * set = nullptr;
+  ~DbMirror() { if (set != nullptr) { vsg_seqset_destroy(set); } }
 };
 std::mutex g_mutex;
-DbMirror g_mirror;
+std::shared_ptr<DbMirror> g_mirror;
 
 int device_ordinal()
 {
@@ -56,26 +59,26 @@ void die(const char * what)
   fatal(m.c_str());
 }
 
-vsg_seqset * mirror_of(vsg_ctx * ctx, Database const & db)
+std::shared_ptr<DbMirror> mirror_of(vsg_ctx * ctx, Database const & db)
 {
   std::lock_guard<std::mutex> const lock(g_mutex);
   uint64_t const n = db.getsequencecount();
   char const * const first = n > 0 ? db.getsequence(0) : nullptr;
-  if (g_mirror.set != nullptr && g_mirror.db == &db && g_mirror.count == n && g_mirror.first == first &&
-      g_mirror.nucleotides == db.getnucleotidecount()) {
-    return g_mirror.set;
+  if (g_mirror && g_mirror->db == &db && g_mirror->count == n && g_mirror->first == first &&
+      g_mirror->nucleotides == db.getnucleotidecount()) {
+    return g_mirror;
   }
-  if (g_mirror.set != nullptr) { vsg_seqset_destroy(g_mirror.set); g_mirror.set = nullptr; }
   std::vector<int64_t> off(n);
   std::vector<int32_t> len(n);
   uint64_t total = 0;
   for (uint64_t i = 0; i < n; i++) { off[i] = static_cast<int64_t>(total); len[i] = static_cast<int32_t>(db.getsequencelen(i)); total += db.getsequencelen(i); }
   std::vector<char> cat(total + 1);
   for (uint64_t i = 0; i < n; i++) { std::memcpy(cat.data() + off[i], db.getsequence(i), static_cast<size_t>(len[i])); }
-  vsg_seqset * s = nullptr;
-  if (vsg_seqset_create(ctx, cat.data(), off.data(), len.data(), static_cast<int64_t>(n), 1, &s) != VSG_OK) { die("vsg_seqset_create"); }
-  g_mirror.db = &db; g_mirror.count = n; g_mirror.first = first; g_mirror.nucleotides = db.getnucleotidecount(); g_mirror.set = s;
-  return s;
+  auto m = std::make_shared<DbMirror>();
+  if (vsg_seqset_create(ctx, cat.data(), off.data(), len.data(), static_cast<int64_t>(n), 1, &m->set) != VSG_OK) { die("vsg_seqset_create"); }
+  m->db = &db; m->count = n; m->first = first; m->nucleotides = db.getnucleotidecount();
+  g_mirror = m;   // the previous mirror goes away when its last user lets go of it
+  return m;
 }
 
 }  // namespace
@@ -127,7 +130,8 @@ auto search16(s16info_s * s, unsigned int sequences, unsigned int const * seqnos
               struct Database const & db) -> void
 {
   if (sequences == 0) { return; }
-  vsg_seqset * const targets = mirror_of(s->ctx, db);
+  std::shared_ptr<DbMirror> const mirror = mirror_of(s->ctx, db);   // held for the duration of the call
+  vsg_seqset * const targets = mirror->set;
   std::vector<uint32_t> qidx(sequences, 0U);
   int64_t cap = 16;
   for (unsigned int i = 0; i < sequences; i++) { cap += static_cast<int64_t>(s->qlen) + static_cast<int64_t>(db.getsequencelen(seqnos[i])) + 2; }

@@ -654,6 +654,7 @@ int rank_enqueue(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * queries, 
 {
   if (tophits < 1 || tophits > TOPHITS_MAX) { Error::set("vsg_rank: tophits must be in 1..1024"); return VSG_EINVAL; }
   if (q0 < 0 || nq < 0 || q0 + nq > queries->d.n) { Error::set("vsg_rank: query range out of bounds"); return VSG_EINVAL; }
+  if (queries->device != c->device || ix->device != c->device) { Error::set("vsg_rank: sequence set / index lives on another device than the context"); return VSG_EINVAL; }
   if (nq > (1 << 30) / tophits) { Error::set("vsg_rank: batch too large"); return VSG_EINVAL; }
   size_t const cells = static_cast<size_t>(nq) * tophits;
   int rc;

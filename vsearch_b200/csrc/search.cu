@@ -213,12 +213,13 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
 
     int64_t const bn = std::min(bn_req, nq - b0);
     vsg_seqset * rc_set = nullptr;
+    struct RcGuard { vsg_seqset *& s; ~RcGuard() { if (s != nullptr) { vsg_seqset_destroy(s); s = nullptr; } } } rc_guard{rc_set};   // every exit
     if (nstrands == 2) {
       int r = seqset_revcomp(c, queries, q0 + b0, bn, &rc_set);
       if (r != VSG_OK) { return r; }
       // each strand is masked on its own (search.cpp:437-449); dust() upper-cases first, so the case the
       // reverse complement inherited from the masked plus strand does not matter
-      if (opts->qmask_dust != 0 && (r = vsg_seqset_dust(c, rc_set)) != VSG_OK) { vsg_seqset_destroy(rc_set); return r; }
+      if (opts->qmask_dust != 0 && (r = vsg_seqset_dust(c, rc_set)) != VSG_OK) { return r; }
     }
     size_t const cells = static_cast<size_t>(bn) * tophits;
     h_seqno.resize(cells * nstrands); h_count.resize(cells * nstrands); h_n.resize(static_cast<size_t>(bn) * nstrands);
@@ -235,13 +236,13 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
       const vsg_seqset * qset = (s == 0) ? queries : rc_set;
       int64_t const qq0 = (s == 0) ? q0 + b0 : 0;
       int r = rank_enqueue(c, ix, qset, qq0, bn, minwordmatches, tophits, opts->mask_lower, &d_seqno, &d_count, &d_n, &d_status);
-      if (r != VSG_OK) { if (rc_set) { vsg_seqset_destroy(rc_set); } return r; }
+      if (r != VSG_OK) { return r; }
       int32_t status = 0;
       VSG_CUDA_OK(cudaMemcpyAsync(h_seqno.data() + cells * s, d_seqno, sizeof(uint32_t) * cells, cudaMemcpyDeviceToHost, c->stream));
       VSG_CUDA_OK(cudaMemcpyAsync(h_count.data() + cells * s, d_count, sizeof(uint32_t) * cells, cudaMemcpyDeviceToHost, c->stream));
       VSG_CUDA_OK(cudaMemcpyAsync(h_n.data() + bn * s, d_n, sizeof(int32_t) * bn, cudaMemcpyDeviceToHost, c->stream));
       if (content_filters) {
-        if ((r = c->pre_flags.reserve(cells + 16)) != VSG_OK) { if (rc_set) { vsg_seqset_destroy(rc_set); } return r; }
+        if ((r = c->pre_flags.reserve(cells + 16)) != VSG_OK) { return r; }
         VSG_CUDA_OK(cudaMemsetAsync(c->pre_flags.p, 0, cells, c->stream));
         int64_t const nwarps = bn * tophits;
         prefilter_kernel<<<static_cast<unsigned>((nwarps * 32 + 255) / 256), 256, 0, c->stream>>>(
@@ -254,7 +255,6 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
       VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
       rank_collect_time(c);
       if (status != 0) {
-        if (rc_set) { vsg_seqset_destroy(rc_set); }
         Error::set("vsg_search_batch: a query is longer than the device ranker supports (65 534 + wordlength nt)");
         return VSG_EINVAL;
       }
@@ -464,7 +464,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
         t_score.resize(nc); t_al.resize(nc); t_ma.resize(nc); t_mi.resize(nc); t_ga.resize(nc); t_tr.resize(nc * 4);
         int const r = device_align(nl, lq.data(), lt.data(), lstate.data(), l_score.data(), l_al.data(), l_ma.data(),
                                    l_mi.data(), l_ga.data(), l_tr.data());
-        if (r != VSG_OK) { if (rc_set) { vsg_seqset_destroy(rc_set); } return r; }
+        if (r != VSG_OK) { return r; }
         for (size_t k = 0; k < nl; k++) {
           if (ldest[k] >= 0) {
             size_t const d = static_cast<size_t>(ldest[k]);
@@ -481,7 +481,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
       } else {
         int const r = device_align(np, pq.data(), pt.data(), pstate.data(), a_score.data(), a_al.data(), a_ma.data(),
                                    a_mi.data(), a_ga.data(), a_tr.data());
-        if (r != VSG_OK) { if (rc_set) { vsg_seqset_destroy(rc_set); } return r; }
+        if (r != VSG_OK) { return r; }
         al_pairs += static_cast<int64_t>(np);
       }
       if (!lazy) { total_pairs += static_cast<int64_t>(np); }
@@ -515,8 +515,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
               // the reference's LinearMemoryAligner path (searchcore.cpp:806-832), host side of the boundary
               if (parent->fallback == nullptr ||
                   parent->fallback(parent->fallback_user, q0 + b0 + ql, strand, h.target, fb) != 0) {
-                if (rc_set) { vsg_seqset_destroy(rc_set); }
-                Error::set("vsg_search_batch: a pair was deferred to the linear-memory aligner (core/linmemalign.cpp) "
+                        Error::set("vsg_search_batch: a pair was deferred to the linear-memory aligner (core/linmemalign.cpp) "
                            "and no vsg_ctx_set_fallback callback resolved it");
                 return VSG_EINVAL;
               }
@@ -578,7 +577,6 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
       }
       counts[b0 + q] = n;
     }
-    if (rc_set) { vsg_seqset_destroy(rc_set); }
     t_join += ms(tp0, now());
   }
   if (trace) {

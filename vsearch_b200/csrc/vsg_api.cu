@@ -98,6 +98,13 @@ int PinBuf::reserve(size_t bytes)
 }
 void PinBuf::release() { if (p != nullptr) { cudaFreeHost(p); p = nullptr; cap = 0; } }
 
+// scope guards for the error paths (VSG_CUDA_OK returns from the middle of a function)
+namespace {
+struct ScopedBuf { DevBuf b; ~ScopedBuf() { b.release(); } };
+struct SeqsetGuard { vsg_seqset * s; ~SeqsetGuard() { if (s != nullptr) { vsg_seqset_destroy(s); } } vsg_seqset * release() { vsg_seqset * r = s; s = nullptr; return r; } };
+struct CtxGuard { vsg_ctx * c; ~CtxGuard() { if (c != nullptr) { vsg_ctx_destroy(c); } } vsg_ctx * release() { vsg_ctx * r = c; c = nullptr; return r; } };
+}  // namespace
+
 // ---- scoring ---------------------------------------------------------------------------------
 static int16_t clamp_cell(int64_t v, int64_t limit, bool & fb)
 {
@@ -222,6 +229,7 @@ extern "C" int vsg_ctx_create(int device, const vsg_scoring * scoring, vsg_ctx *
   VSG_CUDA_OK(cudaSetDevice(device));
   vsg_ctx * c = new (std::nothrow) vsg_ctx();
   if (c == nullptr) { Error::set("out of host memory"); return VSG_ENOMEM; }
+  CtxGuard guard{c};
   c->device = device;
   c->scoring = *scoring;
   build_score_params(*scoring, c->sp);
@@ -232,6 +240,13 @@ extern "C" int vsg_ctx_create(int device, const vsg_scoring * scoring, vsg_ctx *
   c->fast_disabled = (df != nullptr && df[0] == '1');
   const char * db = std::getenv("VSG_DIR_BUDGET_MB");
   if (db != nullptr && std::atoll(db) > 0) { c->dir_budget = static_cast<size_t>(std::atoll(db)) << 20; }
+  else {
+    // scratch for direction bits / checkpoints: at most 64 GiB, and no more than 40 % of what the device has free
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > 0) {
+      c->dir_budget = std::max<size_t>(std::min<size_t>(c->dir_budget, free_b / 5 * 2), static_cast<size_t>(256) << 20);
+    }
+  }
   VSG_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto & ev : c->ev) { VSG_CUDA_OK(cudaEventCreate(&ev)); }
   // the fast kernel leans on VIMNMX.S16x2 predicate semantics: check them on this device once
@@ -244,11 +259,10 @@ extern "C" int vsg_ctx_create(int device, const vsg_scoring * scoring, vsg_ctx *
   VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
   cudaFree(d_bad);
   if (bad != 0) {
-    Error::set("DPX self-test failed (code " + std::to_string(bad) + "): __vibmax_s16x2/__vadd2 semantics differ");
-    vsg_ctx_destroy(c);
+    Error::set("DPX self-test failed (code " + std::to_string(bad) + "): __vibmax_u16x2/__vadd2/__viaddmax_u16x2/__vimax3_u16x2 semantics differ");
     return VSG_ECUDA;
   }
-  *out = c;
+  *out = guard.release();
   return VSG_OK;
 }
 
@@ -298,6 +312,7 @@ extern "C" int vsg_seqset_create(vsg_ctx * c, const char * cat, const int64_t * 
   VSG_CUDA_OK(cudaSetDevice(c->device));
   vsg_seqset * s = new (std::nothrow) vsg_seqset();
   if (s == nullptr) { Error::set("out of host memory"); return VSG_ENOMEM; }
+  SeqsetGuard guard{s};   // destroys s on every early return
   s->device = c->device;
   s->h_len.resize(static_cast<size_t>(n));
   std::vector<int64_t> h_off(static_cast<size_t>(n));
@@ -313,7 +328,7 @@ extern "C" int vsg_seqset_create(vsg_ctx * c, const char * cat, const int64_t * 
   }
   int64_t total = 0;
   for (int64_t i = 0; i < n; i++) {
-    if (s->h_len[i] < 0 || h_off[i] < 0) { delete s; Error::set("vsg_seqset_create: negative length/offset"); return VSG_EINVAL; }
+    if (s->h_len[i] < 0 || h_off[i] < 0) { Error::set("vsg_seqset_create: negative length/offset"); return VSG_EINVAL; }
     total = std::max<int64_t>(total, h_off[i] + s->h_len[i]);
   }
   s->total = total;
@@ -322,13 +337,13 @@ extern "C" int vsg_seqset_create(vsg_ctx * c, const char * cat, const int64_t * 
   if ((rc = s->b_sym.reserve(static_cast<size_t>(total) + 64)) != VSG_OK ||
       (rc = s->b_off.reserve(sizeof(int64_t) * static_cast<size_t>(n) + 8)) != VSG_OK ||
       (rc = s->b_len.reserve(sizeof(int32_t) * static_cast<size_t>(n) + 8)) != VSG_OK) {
-    vsg_seqset_destroy(s);
     return rc;
   }
   const char * d_ascii = cat;
-  DevBuf tmp_ascii;
+  ScopedBuf tmp_ascii_g;
+  DevBuf & tmp_ascii = tmp_ascii_g.b;
   if (host != 0 && total > 0) {
-    if ((rc = tmp_ascii.reserve(static_cast<size_t>(total))) != VSG_OK) { vsg_seqset_destroy(s); return rc; }
+    if ((rc = tmp_ascii.reserve(static_cast<size_t>(total))) != VSG_OK) { return rc; }
     VSG_CUDA_OK(cudaMemcpyAsync(tmp_ascii.p, cat, static_cast<size_t>(total), cudaMemcpyHostToDevice, c->stream));
     d_ascii = static_cast<const char *>(tmp_ascii.p);
   }
@@ -347,8 +362,9 @@ extern "C" int vsg_seqset_create(vsg_ctx * c, const char * cat, const int64_t * 
     count_launch();
   }
   if (n > 0) {
-    DevBuf flag;
-    if ((rc = flag.reserve(static_cast<size_t>(n))) != VSG_OK) { vsg_seqset_destroy(s); return rc; }
+    ScopedBuf flag_g;
+    DevBuf & flag = flag_g.b;
+    if ((rc = flag.reserve(static_cast<size_t>(n))) != VSG_OK) { return rc; }
     int64_t const blocks = (n * 32 + 255) / 256;
     nonacgt_kernel<<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(s->d, static_cast<uint8_t *>(flag.p));
     count_launch();
@@ -360,7 +376,7 @@ extern "C" int vsg_seqset_create(vsg_ctx * c, const char * cat, const int64_t * 
   }
   tmp_ascii.release();
   VSG_CUDA_OK(cudaGetLastError());
-  *out = s;
+  *out = guard.release();
   return VSG_OK;
 }
 
@@ -378,6 +394,7 @@ int seqset_revcomp(vsg_ctx * c, const vsg_seqset * src, int64_t q0, int64_t n, v
   *out = nullptr;
   vsg_seqset * s = new (std::nothrow) vsg_seqset();
   if (s == nullptr) { Error::set("out of host memory"); return VSG_ENOMEM; }
+  SeqsetGuard guard{s};
   s->device = c->device;
   s->h_len.assign(src->h_len.begin() + q0, src->h_len.begin() + q0 + n);
   s->h_nonacgt.assign(src->h_nonacgt.begin() + q0, src->h_nonacgt.begin() + q0 + n);
@@ -390,7 +407,6 @@ int seqset_revcomp(vsg_ctx * c, const vsg_seqset * src, int64_t q0, int64_t n, v
   if ((rc = s->b_sym.reserve(static_cast<size_t>(total) + 64)) != VSG_OK ||
       (rc = s->b_off.reserve(sizeof(int64_t) * static_cast<size_t>(n) + 8)) != VSG_OK ||
       (rc = s->b_len.reserve(sizeof(int32_t) * static_cast<size_t>(n) + 8)) != VSG_OK) {
-    vsg_seqset_destroy(s);
     return rc;
   }
   s->d.sym = static_cast<uint8_t *>(s->b_sym.p);
@@ -405,7 +421,7 @@ int seqset_revcomp(vsg_ctx * c, const vsg_seqset * src, int64_t q0, int64_t n, v
     count_launch();
     VSG_CUDA_OK(cudaStreamSynchronize(c->stream));  // h_off goes out of scope
   }
-  *out = s;
+  *out = guard.release();
   return VSG_OK;
 }
 }  // namespace vsg
@@ -546,6 +562,7 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
     return VSG_EINVAL;
   }
   if (npairs > (1LL << 30)) { Error::set("vsg_align_pairs: too many pairs in one call"); return VSG_EINVAL; }
+  if (queries->device != c->device || targets->device != c->device) { Error::set("vsg_align_pairs: sequence set lives on another device than the context"); return VSG_EINVAL; }
   VSG_CUDA_OK(cudaSetDevice(c->device));
   static const bool trace = std::getenv("VSG_TRACE") != nullptr;
   auto const t_begin = std::chrono::steady_clock::now();
