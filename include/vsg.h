@@ -141,8 +141,9 @@ typedef struct vsg_profile {
 } vsg_profile;
 int vsg_profile_reset(vsg_ctx * ctx);
 int vsg_profile_get(vsg_ctx * ctx, vsg_profile * out);
-/* Measured integer-pipe peak of this device: packed 16x2 ALU lane-operations per second
- * (VIMNMX.S16x2 / VIADD.16x2 mix with no memory traffic), the denominator of the DP roofline. */
+/* Measured integer issue peak of this device: thread-instructions per second of an even mix of packed 16x2 DPX
+ * (ALU pipe) and 32-bit multiply-add (FMA pipe) instructions with no memory traffic — each processes the two
+ * packed cells of a register, so 2 x this / (instructions per cell pair) is the DP roofline's denominator. */
 int vsg_measure_int_peak(vsg_ctx * ctx, double * packed_lane_ops_per_s);
 
 /* ---- k-mer index: replaces Dbindex::prepare + add_all_sequences + the getters

@@ -906,16 +906,24 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
 }
 
 namespace vsg {
-// independent chains of the two packed instructions the forward kernel is made of
-__global__ void int_peak_kernel(uint32_t * out, uint32_t seed, int iters)
+// Integer issue peak of an SM: independent chains, half of them a packed DPX instruction (VIADDMNMX.U16x2, ALU
+// pipe), half a 32-bit multiply-add (IMAD, FMA pipe) — the mix the checkpoint forward kernel is made of.  Each pipe
+// alone issues 0.5 warp-instructions per clock per SM sub-partition, together they reach the issue limit of 1
+// (tools/pipe_probe.cu, profiles/pipe_probe_r02.txt).  Operands come from the other chains so that nothing folds.
+__global__ void int_peak_kernel(uint32_t * out, uint32_t seed, uint32_t one, int iters)
 {
   uint32_t a[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) { a[k] = seed * (threadIdx.x + 1) + k * 0x00030005u; }
-  uint32_t const c1 = seed | 0x00010001u, c2 = seed ^ 0x00070003u;
   for (int it = 0; it < iters; it++) {
+    uint32_t n[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) { a[k] = __vmaxs2(__vadd2(a[k], c1), c2); }
+    for (int k = 0; k < 8; k++) {
+      if (k & 1) { asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(n[k]) : "r"(a[k]), "r"(one), "r"(a[(k + 2) & 7])); }
+      else { n[k] = __viaddmax_u16x2(a[k], a[(k + 2) & 7], a[(k + 4) & 7]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) { a[k] = n[k]; }
   }
   uint32_t r = 0;
 #pragma unroll
@@ -936,13 +944,13 @@ extern "C" int vsg_measure_int_peak(vsg_ctx * c, double * packed_lane_ops_per_s)
   double best = 0.0;
   for (int rep = 0; rep < 4; rep++) {
     VSG_CUDA_OK(cudaEventRecord(c->ev[4], c->stream));
-    int_peak_kernel<<<blocks, threads, 0, c->stream>>>(static_cast<uint32_t *>(c->cub_tmp.p), 3u + rep, iters);
+    int_peak_kernel<<<blocks, threads, 0, c->stream>>>(static_cast<uint32_t *>(c->cub_tmp.p), 3u + rep, 1u, iters);
     count_launch();
     VSG_CUDA_OK(cudaEventRecord(c->ev[5], c->stream));
     VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
-    double const ops = 2.0 * 8.0 * iters * static_cast<double>(threads) * blocks;  // 2 packed ops per statement
+    double const ops = 8.0 * iters * static_cast<double>(threads) * blocks;  // one instruction per chain and iteration
     if (rep > 0) { best = std::max(best, ops / (ms * 1e-3)); }
   }
   *packed_lane_ops_per_s = best;
