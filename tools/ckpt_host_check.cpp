@@ -170,8 +170,9 @@ int main(int argc, char ** argv)
         std::string rev;
         HostBits bits;
         HostRows rows{rowck.data()};
-        if (R <= 8) { traceback<8>(sp, pv, bits, rows, out, [&](char o) { rev.push_back(o); }); }
-        else { traceback<16>(sp, pv, bits, rows, out, [&](char o) { rev.push_back(o); }); }
+        auto emit = [&](char o, int cnt) { rev.append(static_cast<size_t>(cnt), o); };
+        if (R <= 8) { if (general) { traceback<8, true>(sp, pv, bits, rows, out, emit); } else { traceback<8, false>(sp, pv, bits, rows, out, emit); } }
+        else { if (general) { traceback<16, true>(sp, pv, bits, rows, out, emit); } else { traceback<16, false>(sp, pv, bits, rows, out, emit); } }
         int16_t os; uint16_t oa, om, omi, og;
         std::vector<char> cig(Q + DD + 64);
         if (oracle_nw16(&sc, qs.data(), Q, ts[hh].data(), DD, &os, &oa, &om, &omi, &og, cig.data(), cig.size()) != 0) { std::fprintf(stderr, "oracle_nw16 failed\n"); return 2; }

@@ -387,7 +387,9 @@ __device__ __forceinline__ void traceback_ckpt_one(const ScoreParams & sp, const
   if (TEXT) { *--cw.end = 0; }
   cw.op = 0; cw.run = 0; cw.len = 0;
   ckpt::TbOut o;
-  ckpt::traceback<RT>(sp, pv, bits, rows, o, [&](char nop) { if (TEXT) { cw.push(nop); } });
+  auto emit = [&](char nop, int n) { if (TEXT) { cw.push_n(nop, n); } };
+  if (general) { ckpt::traceback<RT, true>(sp, pv, bits, rows, o, emit); }
+  else { ckpt::traceback<RT, false>(sp, pv, bits, rows, o, emit); }
   if (TEXT) { cw.flush(); }
   st[VSG_STAT_ALIGNED] = o.aligned; st[VSG_STAT_MATCHES] = o.matches; st[VSG_STAT_MISMATCHES] = o.mismatches;
   st[VSG_STAT_GAPS] = o.gaps; st[VSG_STAT_TRIM_LEFT] = o.trim_left; st[VSG_STAT_TRIM_RIGHT] = o.trim_right;

@@ -602,6 +602,13 @@ struct CigarWriter {
     op = o;
     run = 1;
   }
+  __device__ __forceinline__ void push_n(char o, int n)
+  {
+    if (o == op) { run += n; return; }
+    if (text) { flush(); }
+    op = o;
+    run = n;
+  }
 };
 
 template <bool TEXT>

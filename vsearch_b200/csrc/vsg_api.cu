@@ -157,6 +157,7 @@ static bool shifted_params(const ScoreParams & p, ScoreParams & q)
   for (int k = 0; k < 6; k++) { q.ge[k] = fit(p.ge[k] + c); }
   q.match = fit(p.match - 2 * c);
   q.mismatch = fit(p.mismatch - 2 * c);
+  if (q.match < q.mismatch) { ok = false; }   // tb_ckpt.h scores ACGT pairs as mismatch + e * (match - mismatch)
   return ok;
 }
 
