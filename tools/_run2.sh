@@ -1,3 +1,3 @@
 mkdir -p gpurun_out/tb2
-ncu --set full --import-source on --clock-control none --kernel-name-base mangled -k regex:traceback_ckpt_tasks_kernelILi8 -s 2 -c 1 -o gpurun_out/tb2/tbckpt2 python tools/stage_times.py 16384 --short > gpurun_out/tb2/log.txt 2>&1
-tail -3 gpurun_out/tb2/log.txt
+for r in 0; do echo "refill=$r"; VSG_TB_REFILL=$r python tools/stage_times.py 16384 --short 2>&1 | tail -1; done
+python -m pytest tests/test_align_gpu.py tests/test_stress_gpu.py tests/test_scale_gpu.py -x -q 2>&1 | tail -2

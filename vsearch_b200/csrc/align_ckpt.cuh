@@ -325,6 +325,12 @@ struct SmemBits {
   uint32_t * base;   // this thread's first word
   __device__ __forceinline__ void set(int bj, int k, uint32_t v) { base[(bj * NW + k) * TB_CK_THREADS] = v; }
   __device__ __forceinline__ uint32_t get(int bj, int k) const { return base[(bj * NW + k) * TB_CK_THREADS]; }
+  __device__ __forceinline__ void stage_word(int bj, const uint8_t * t, int, int mis, int wi)
+  {
+    uint32_t const dst = static_cast<uint32_t>(__cvta_generic_to_shared(base + (bj * NW) * TB_CK_THREADS));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(reinterpret_cast<const uint32_t *>(t - mis) + wi) : "memory");
+  }
+  __device__ __forceinline__ void wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 };
 
 // Row checkpoints of one tile staged in shared memory: the (at most ten) 32-byte sectors that hold the tile's
@@ -396,23 +402,72 @@ __device__ __forceinline__ void traceback_ckpt_one(const ScoreParams & sp, const
   st[VSG_STAT_CIGARLEN] = TEXT ? cw.len : 0;
 }
 
-// statistics-only, straight from the forward tasks: thread 2k / 2k+1 = first / second target of task k
+// statistics-only, straight from the forward tasks: pair 2k / 2k+1 = first / second target of task k.
+// Alignments differ a lot in the number of tiles their paths cross (the end gap of a short query in a long target
+// alone is up to D/32 tiles), so a thread does not own one pair: the grid is sized to fill the device once, every
+// thread starts with pair = its global index and, whenever its alignment is finished, takes the next unclaimed pair
+// from a ticket counter while the other lanes of its warp carry on with theirs.  *ticket must be 0 at launch.
+template <int RT, bool GENERAL>
+__device__ __forceinline__ void traceback_ckpt_tasks_body(const ScoreParams & sp, const DevSeqs & qs, const DevSeqs & ts,
+                                                          const FastTask * __restrict__ tasks, int ntasks, int R,
+                                                          const uint2 * __restrict__ rowck, const uint2 * __restrict__ colck,
+                                                          int32_t * __restrict__ stats, int * __restrict__ ticket, int ticket_base,
+                                                          unsigned char * smem)
+{
+  int const total = 2 * ntasks;
+  int const nthreads = gridDim.x * blockDim.x;
+  SmemRows rows{nullptr, reinterpret_cast<uint4 *>(smem) + threadIdx.x};
+  SmemBits<RT / 8> bits{reinterpret_cast<uint32_t *>(smem + static_cast<size_t>(TB_CK_ROWVECS) * TB_CK_THREADS * 16) + threadIdx.x};
+  auto emit = [](char, int) {};
+  ckpt::Walk<RT, GENERAL> w;
+  int next = blockIdx.x * blockDim.x + threadIdx.x;
+  int out = -1;
+  bool active = false;
+  for (;;) {
+    while (!active && next < total) {
+      int const id = next;
+      FastTask const tk = tasks[id >> 1];
+      int const half = id & 1;
+      out = half ? tk.out_hi : tk.out_lo;
+      next = ticket_base >= total ? total : nthreads + atomicAdd(ticket, 1);
+      if (out < 0) { continue; }
+      uint32_t const q = tk.q, t = half ? tk.thi : tk.tlo;
+      ckpt::PairView pv;
+      pv.rowck = reinterpret_cast<const ckpt::U2 *>(rowck + tk.dir_off);
+      pv.colck = reinterpret_cast<const ckpt::U2 *>(colck + tk.bnd_off);
+      pv.R = R; pv.half = half; pv.Q = qs.len[q]; pv.D = ts.len[t]; pv.general = GENERAL ? 1 : 0;
+      pv.q = qs.sym + qs.off[q];
+      pv.t = ts.sym + ts.off[t];
+      rows.rowck = rowck + tk.dir_off;
+      w.start(pv);
+      active = true;
+    }
+    if (!__any_sync(0xffffffffu, active)) { break; }
+    if (active) {
+      if (w.running()) { w.round(sp, bits, rows, emit); }
+      if (!w.running()) {
+        ckpt::TbOut o;
+        w.finish(o, emit);
+        int32_t * const st = stats + static_cast<size_t>(out) * VSG_STAT_WORDS;
+        st[VSG_STAT_ALIGNED] = o.aligned; st[VSG_STAT_MATCHES] = o.matches; st[VSG_STAT_MISMATCHES] = o.mismatches;
+        st[VSG_STAT_GAPS] = o.gaps; st[VSG_STAT_TRIM_LEFT] = o.trim_left; st[VSG_STAT_TRIM_RIGHT] = o.trim_right;
+        st[VSG_STAT_CIGARLEN] = 0;
+        active = false;
+      }
+    }
+  }
+}
+
 template <int RT>
 __global__ void __launch_bounds__(TB_CK_THREADS)
 traceback_ckpt_tasks_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
                             const FastTask * __restrict__ tasks, int ntasks, int R, int general,
                             const uint2 * __restrict__ rowck, const uint2 * __restrict__ colck,
-                            int32_t * __restrict__ stats)
+                            int32_t * __restrict__ stats, int * __restrict__ ticket, int ticket_base)
 {
   extern __shared__ __align__(16) unsigned char tb_smem[];
-  int const id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= 2 * ntasks) { return; }
-  FastTask const tk = tasks[id >> 1];
-  int const half = id & 1;
-  int const out = half ? tk.out_hi : tk.out_lo;
-  if (out < 0) { return; }
-  traceback_ckpt_one<RT, false>(sp, qs, ts, tk.q, half ? tk.thi : tk.tlo, out, R, half, general,
-                                rowck + tk.dir_off, colck + tk.bnd_off, nullptr, stats, tb_smem);
+  if (general) { traceback_ckpt_tasks_body<RT, true>(sp, qs, ts, tasks, ntasks, R, rowck, colck, stats, ticket, ticket_base, tb_smem); }
+  else { traceback_ckpt_tasks_body<RT, false>(sp, qs, ts, tasks, ntasks, R, rowck, colck, stats, ticket, ticket_base, tb_smem); }
 }
 
 // with CIGAR text, from pair descriptors (kind 2 = checkpoint layout; the others belong to traceback_kernel)

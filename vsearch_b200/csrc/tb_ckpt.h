@@ -24,8 +24,10 @@
 #endif
 #ifdef __CUDA_ARCH__
 #define VSG_CKPT_UNROLL _Pragma("unroll")
+#define VSG_CKPT_NOUNROLL _Pragma("unroll 1")
 #else
 #define VSG_CKPT_UNROLL
+#define VSG_CKPT_NOUNROLL
 #endif
 
 namespace vsg {
@@ -66,6 +68,9 @@ struct HostBits {
   uint32_t w[CHUNK][RMAX / 8];
   void set(int bj, int k, uint32_t v) { w[bj][k] = v; }
   uint32_t get(int bj, int k) const { return w[bj][k]; }
+  // slot (bj, 0) <- word wi of the target's aligned symbol window (see Walk::round); asynchronous on the device
+  void stage_word(int bj, const uint8_t * t, int D, int mis, int wi);
+  void wait() {}
 };
 
 // Rows: access to the row checkpoints of one lane for a tile's steps.  stage(l, s0, s1) announces the range
@@ -168,19 +173,7 @@ VSG_CKPT_HD uint32_t sym_word(const uint8_t * t, int D, int mis, int w)
 #endif
 }
 
-// dst = sym_word(...) where `take` holds.  On the device the load is predicated and writes dst in place: written as
-// a conditional assignment, ptxas loads into a temporary and copies it into the ring in the same step, which makes
-// every fourth step wait for a full memory latency.
-VSG_CKPT_HD void sym_word_if(uint32_t & dst, bool take, const uint8_t * t, int D, int mis, int w)
-{
-#ifdef __CUDA_ARCH__
-  (void)D;
-  asm volatile("{.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];}"
-               : "+r"(dst) : "l"(reinterpret_cast<const uint32_t *>(t - mis) + w), "r"(static_cast<uint32_t>(take)));
-#else
-  if (take) { dst = sym_word(t, D, mis, w); }
-#endif
-}
+inline void HostBits::stage_word(int bj, const uint8_t * t, int D, int mis, int wi) { w[bj][0] = sym_word(t, D, mis, wi); }
 
 // emit(op, n) receives the alignment's operations last to first as runs ('M', 'I' = column consumed alone,
 // 'D' = row consumed alone; consecutive calls may carry the same op).  SP supplies S[16][16], go[6], ge[6], match,
@@ -196,9 +189,47 @@ VSG_CKPT_HD void sym_word_if(uint32_t & dst, bool take, const uint8_t * t, int D
 // and the halves that can hold garbage (rows below the entry row: always the HIGH half of an operation whose low
 // half is real, or both) can only borrow out of bit 31.
 // GENERAL: a symbol outside ACGT in either sequence (scores from the 16x16 table instead of match / mismatch).
-template <int RT, bool GENERAL, class SP, class Bits, class Rows, class Emit>
-VSG_CKPT_HD void traceback(const SP & sp, const PairView & v, Bits & bits, Rows & rows, TbOut & out, Emit && emit)
-{
+// One alignment's traceback as a resumable object: start(), then round() once per tile while running(), then
+// finish().  The kernels keep one of these per thread; a thread whose alignment is finished can start the next one
+// while its warp's other lanes are still in the middle of theirs (align_ckpt.cuh).
+template <int RT, bool GENERAL>
+struct Walk {
+  PairView v;
+  int i, j, b, i0;
+  char op;
+  int aligned, matches, mismatches, gaps;
+  char last_run_op; int last_run; bool last_open;   // the run that ENDS the alignment
+  char first_op; int first_run;                     // the run still open = the alignment's first
+
+  VSG_CKPT_HD void start(const PairView & pv)
+  {
+    v = pv;
+    i = v.Q - 1; j = v.D - 1;
+    b = i / v.R; i0 = b * v.R;
+    op = 0;
+    aligned = 0; matches = 0; mismatches = 0; gaps = 0;
+    last_run_op = 0; last_run = 0; last_open = true;
+    first_op = 0; first_run = 0;
+  }
+  VSG_CKPT_HD bool running() const { return i >= 0 && j >= 0; }
+
+  template <class Emit>
+  VSG_CKPT_HD void push(Emit & emit, char nop, int n)
+  {
+    aligned += n;
+    if (last_open) {
+      if (last_run == 0 || nop == last_run_op) { last_run_op = nop; last_run += n; }
+      else { last_open = false; }
+    }
+    if (nop == first_op) { first_run += n; } else { first_op = nop; first_run = n; }
+    emit(nop, n);
+    op = nop;
+  }
+
+  // regenerate the tile the path is about to enter and walk through it
+  template <class SP, class Bits, class Rows, class Emit>
+  VSG_CKPT_HD void round(const SP & sp, Bits & bits, Rows & rows, Emit & emit)
+  {
   constexpr int RH = RT / 2;
   constexpr uint32_t B = 0x8000u;
   int const R = v.R, Q = v.Q, D = v.D, sh = 16 * v.half;
@@ -211,24 +242,6 @@ VSG_CKPT_HD void traceback(const SP & sp, const PairView & v, Bits & bits, Rows 
   uint32_t const ds = static_cast<uint32_t>(static_cast<int>(sp.match) - static_cast<int>(sp.mismatch));
   auto half_of = [&](uint32_t w) { return (w >> sh) & 0xffffu; };   // stays biased
 
-  int i = Q - 1, j = D - 1;
-  int b = i / R, i0 = b * R;
-  char op = 0;
-  int aligned = 0, matches = 0, mismatches = 0, gaps = 0;
-  char last_run_op = 0; int last_run = 0; bool last_open = true;   // the run that ENDS the alignment
-  char first_op = 0; int first_run = 0;                            // the run still open = the alignment's first
-  auto push = [&](char nop, int n) {
-    aligned += n;
-    if (last_open) {
-      if (last_run == 0 || nop == last_run_op) { last_run_op = nop; last_run += n; }
-      else { last_open = false; }
-    }
-    if (nop == first_op) { first_run += n; } else { first_op = nop; first_run = n; }
-    emit(nop, n);
-    op = nop;
-  };
-
-  while (i >= 0 && j >= 0) {
     // ---- regenerate the tile (lane b, chunk k) up to the cell (i, j) ----
     int const k = (j + b) / CHUNK;
     int const jlo = (CHUNK * k - b) > 0 ? (CHUNK * k - b) : 0;
@@ -260,14 +273,20 @@ VSG_CKPT_UNROLL
     // the target's symbols come as aligned words of four, three words in flight
     int const tmis = static_cast<int>(reinterpret_cast<uintptr_t>(v.t) & 3u);
     int const twmax = (D - 1 + tmis) >> 2;
-    int tidx = jlo + tmis;
-    uint32_t twc, twn, twn2;
-    {
-      int const w0 = tidx >> 2;
-      twc = sym_word(v.t, D, tmis, w0);
-      twn = sym_word(v.t, D, tmis, w0 + 1 < twmax ? w0 + 1 : twmax);
-      twn2 = sym_word(v.t, D, tmis, w0 + 2 < twmax ? w0 + 2 : twmax);
-    }
+    // step 0 takes column jlo's symbol; after it the steps run in groups of four that share one 4-symbol word,
+    // funnelled out of two words of the target's aligned symbol window.  The window's words are copied (cp.async on
+    // the device: no registers, nothing waits) into slots of the tile's bit storage that are only written later:
+    // word m of the window, first needed by the group of steps 4m+1 .. 4m+4, sits in column slot 4m+3, which the
+    // regeneration fills at step 4m+3 (RT 16) or 4m+4 (RT 8) — after that group's words have been read.  A ninth
+    // word (second word of the last group when the window is misaligned) stays in a register.
+    int const tg = jlo + 1 + tmis;          // byte offset of step 1's symbol in the aligned window
+    int const tsh = 8 * (tg & 3);
+    int const twi = tg >> 2;
+    uint32_t const t_first = v.t[jlo];
+VSG_CKPT_UNROLL
+    for (int m = 0; m < CHUNK / 4; m++) { bits.stage_word(4 * m + 3, v.t, D, tmis, twi + m < twmax ? twi + m : twmax); }
+    uint32_t const tw_last = sym_word(v.t, D, tmis, twi + CHUNK / 4 < twmax ? twi + CHUNK / 4 : twmax);
+    uint32_t sym4 = t_first;
     uint32_t qpack[RT / 8];
 VSG_CKPT_UNROLL
     for (int w = 0; w < RT / 8; w++) { qpack[w] = 0; }
@@ -291,7 +310,7 @@ VSG_CKPT_UNROLL
       qrq[kk] = pk16(kk == alast ? QRqr : QRqi, kk + RH == alast ? QRqr : QRqi);
       rq[kk] = pk16(kk == alast ? Rqr : Rqi, kk + RH == alast ? Rqr : Rqi);
     }
-    if (b > 0) { rows.wait(); }
+    if (b > 0) { rows.wait(); } else { bits.wait(); }
     // H(i0-1, jlo-1): the diagonal input of the tile's first cell
     uint32_t hd;
     if (b == 0) { hd = jlo == 0 ? B : B - static_cast<uint32_t>(goql + jlo * geql); }
@@ -318,15 +337,8 @@ VSG_CKPT_UNROLL
       uint32_t hdiag = lo_lo(hd, hmid_pp);
       uint32_t f = lo_lo(fin, fmid_p);
       hd = htop;
-      uint32_t const tc = (twc >> (8 * (tidx & 3))) & 15u;
-      {
-        bool const rot = (tidx & 3) == 3;
-        int const w = (tidx >> 2) + 3;
-        twc = rot ? twn : twc;
-        twn = rot ? twn2 : twn;
-        sym_word_if(twn2, rot, v.t, D, tmis, w < twmax ? w : twmax);
-      }
-      tidx++;
+      uint32_t const tc = sym4 & 15u;
+      sym4 >>= 8;
       if (!GENERAL && c < nj) { tsym2 |= static_cast<unsigned long long>((tc >> 1) - (tc >> 3)) << (2 * c); }
       uint32_t const T = tc | (tprev << 16);
       tprev = tc;
@@ -373,7 +385,21 @@ VSG_CKPT_UNROLL
       }
     };
     step(0, ckpt_true{});
-    for (int c = 1; c < nsteps; c++) { step(c, ckpt_false{}); }
+    for (int c = 1; c < nsteps;) {
+      {
+        int const m = (c - 1) >> 2;
+        uint32_t const wa = bits.get(4 * m + 3, 0);
+        uint32_t const wb = m + 1 < CHUNK / 4 ? bits.get(4 * m + 7, 0) : tw_last;
+#ifdef __CUDA_ARCH__
+        sym4 = __funnelshift_r(wa, wb, tsh);
+#else
+        sym4 = tsh == 0 ? wa : ((wa >> tsh) | (wb << (32 - tsh)));
+#endif
+      }
+      int const ce = c + 4 < nsteps ? c + 4 : nsteps;
+VSG_CKPT_NOUNROLL
+      for (; c < ce; c++) { step(c, ckpt_false{}); }
+    }
     if (RT == 8 && nsteps == nj) { bits.set(nj - 1, 0, wprev); }   // no high rows in this tile: the last column's word is still pending
     // ---- walk inside the tile (backtrack16's priorities, align_simd.cpp:1150-1210) ----
     auto nib = [&](int a, int bj) { return (bits.get(bj, RT > 8 ? (a >> 3) : 0) >> (4 * (a & 7))) & 15u; };
@@ -385,7 +411,7 @@ VSG_CKPT_UNROLL
         int n = 1;
         j--;
         while (j >= jlo && (nib(a, j - jlo) & 8u)) { n++; j--; }
-        push('I', n);
+        push(emit, 'I', n);
         continue;
       }
       bool const ext_d = (op == 'D') && (d & 4u);
@@ -402,15 +428,29 @@ VSG_CKPT_UNROLL
       }
       if (!is_i) { i--; }
       if (!is_d) { j--; }
-      push(is_i ? 'I' : (is_d ? 'D' : 'M'), 1);
+      push(emit, is_i ? 'I' : (is_d ? 'D' : 'M'), 1);
     }
     if (i < i0) { b--; i0 -= R; }
   }
-  if (i >= 0) { if (op != 'D') { gaps++; } push('D', i + 1); }
-  if (j >= 0) { if (op != 'I') { gaps++; } push('I', j + 1); }
-  out.aligned = aligned; out.matches = matches; out.mismatches = mismatches; out.gaps = gaps;
-  out.trim_left = first_op == 'D' ? first_run : (first_op == 'I' ? -first_run : 0);
-  out.trim_right = last_run_op == 'D' ? last_run : (last_run_op == 'I' ? -last_run : 0);
+
+  template <class Emit>
+  VSG_CKPT_HD void finish(TbOut & out, Emit & emit)
+  {
+    if (i >= 0) { if (op != 'D') { gaps++; } push(emit, 'D', i + 1); i = -1; }
+    if (j >= 0) { if (op != 'I') { gaps++; } push(emit, 'I', j + 1); j = -1; }
+    out.aligned = aligned; out.matches = matches; out.mismatches = mismatches; out.gaps = gaps;
+    out.trim_left = first_op == 'D' ? first_run : (first_op == 'I' ? -first_run : 0);
+    out.trim_right = last_run_op == 'D' ? last_run : (last_run_op == 'I' ? -last_run : 0);
+  }
+};
+
+template <int RT, bool GENERAL, class SP, class Bits, class Rows, class Emit>
+VSG_CKPT_HD void traceback(const SP & sp, const PairView & v, Bits & bits, Rows & rows, TbOut & out, Emit && emit)
+{
+  Walk<RT, GENERAL> w;
+  w.start(v);
+  while (w.running()) { w.round(sp, bits, rows, emit); }
+  w.finish(out, emit);
 }
 
 }  // namespace ckpt

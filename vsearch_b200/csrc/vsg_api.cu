@@ -276,7 +276,7 @@ extern "C" void vsg_ctx_destroy(vsg_ctx * c)
   if (c->stream != nullptr) { cudaStreamSynchronize(c->stream); }
   for (DevBuf * b : {&c->dir, &c->bnd, &c->he, &c->cigar_scratch, &c->cigar_dense, &c->stats,
                      &c->tasks_fast, &c->tasks_exact, &c->pairs, &c->cigar_len, &c->cigar_offs,
-                     &c->cub_tmp, &c->rank_tmp, &c->rank_scratch, &c->pre_flags}) { b->release(); }
+                     &c->cub_tmp, &c->rank_tmp, &c->rank_scratch, &c->pre_flags, &c->ticket}) { b->release(); }
   for (PinBuf * b : {&c->h_tasks, &c->h_stats}) { b->release(); }
   for (auto & ev : c->ev) { if (ev != nullptr) { cudaEventDestroy(ev); } }
   for (auto & ev : c->ev_pool) { cudaEventDestroy(ev); }
@@ -510,22 +510,37 @@ void launch_ckpt(vsg_ctx * c, int R, bool general, const DevSeqs & qs, const Dev
   }
 }
 
-void launch_tb_ckpt_tasks(vsg_ctx * c, int R, bool general, const DevSeqs & qs, const DevSeqs & ts, const FastTask * d_tasks, int n)
+int launch_tb_ckpt_tasks(vsg_ctx * c, int R, bool general, const DevSeqs & qs, const DevSeqs & ts, const FastTask * d_tasks, int n)
 {
+  // a grid that fills the device once (the kernel hands further pairs out itself), fewer blocks for small calls
+  int rc;
+  if ((rc = c->ticket.reserve(64)) != VSG_OK) { return rc; }
+  VSG_CUDA_OK(cudaMemsetAsync(c->ticket.p, 0, sizeof(int), c->stream));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
   int const nthr = 2 * n;
-  int const blocks = (nthr + TB_CK_THREADS - 1) / TB_CK_THREADS;
+  int const want = (nthr + TB_CK_THREADS - 1) / TB_CK_THREADS;
+  static int const refill = [] { const char * e = std::getenv("VSG_TB_REFILL"); return e != nullptr ? std::atoi(e) : 0; }();
+  int const tbase = refill > 0 ? 0 : nthr;   // >= the number of pairs: every thread does its own pair only
   if (R <= 8) {
     cudaFuncSetAttribute(traceback_ckpt_tasks_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tb_ck_smem(8)));
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, traceback_ckpt_tasks_kernel<8>, TB_CK_THREADS, tb_ck_smem(8));
+    int const blocks = refill > 0 ? std::min(want, std::max(1, per_sm) * sms * refill) : want;
     traceback_ckpt_tasks_kernel<8><<<blocks, TB_CK_THREADS, tb_ck_smem(8), c->stream>>>(
         c->sp2, qs, ts, d_tasks, n, R, general ? 1 : 0, static_cast<const uint2 *>(c->dir.p), static_cast<const uint2 *>(c->bnd.p),
-        static_cast<int32_t *>(c->stats.p));
+        static_cast<int32_t *>(c->stats.p), static_cast<int *>(c->ticket.p), tbase);
   } else {
     cudaFuncSetAttribute(traceback_ckpt_tasks_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tb_ck_smem(16)));
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, traceback_ckpt_tasks_kernel<16>, TB_CK_THREADS, tb_ck_smem(16));
+    int const blocks = refill > 0 ? std::min(want, std::max(1, per_sm) * sms * refill) : want;
     traceback_ckpt_tasks_kernel<16><<<blocks, TB_CK_THREADS, tb_ck_smem(16), c->stream>>>(
         c->sp2, qs, ts, d_tasks, n, R, general ? 1 : 0, static_cast<const uint2 *>(c->dir.p), static_cast<const uint2 *>(c->bnd.p),
-        static_cast<int32_t *>(c->stats.p));
+        static_cast<int32_t *>(c->stats.p), static_cast<int *>(c->ticket.p), tbase);
   }
   count_launch();
+  return VSG_OK;
 }
 
 // A chunk = the tasks whose direction blocks share the scratch buffer at the same time.
@@ -790,7 +805,10 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
     VSG_CUDA_OK(cudaEventRecord(c->ev_pool[3 * ci + 1], c->stream));
     if (!want_cigar) {
       for (auto const & run : pl.runs) {
-        if (run.ckpt) { launch_tb_ckpt_tasks(c, run.R, run.general, queries->d, targets->d, d_fast + run.first, run.count); continue; }
+        if (run.ckpt) {
+          if ((rc = launch_tb_ckpt_tasks(c, run.R, run.general, queries->d, targets->d, d_fast + run.first, run.count)) != VSG_OK) { return rc; }
+          continue;
+        }
         int const nthr = 2 * run.count;
         traceback_fast_tasks_kernel<<<(nthr + 127) / 128, 128, 0, c->stream>>>(sp, queries->d, targets->d, d_fast + run.first,
                                                                                run.count, run.R, d_dir, d_stats);
