@@ -33,9 +33,16 @@ constexpr int RANK_THREADS = 512;
 constexpr int KMER_CAP = 2048;          // distinct-k-mer capacity per query (query length <= 2047 + k)
 constexpr int CAND_CAP = 2048;          // candidate keys held in shared memory
 constexpr int TOPHITS_MAX = 1024;
+constexpr int RANK_PREFETCH = 3;         // k-mers (per warp) between the L2 prefetch of a list and its use
 constexpr int SCAN_SEG_WORDS = 512;     // counters are scanned 1024 at a time (<= 1024 new candidates)
-constexpr uint16_t POST_PAD = 0x8000;   // list padding: counts into a dummy counter word past the shard
 constexpr int COUNTER_WORDS = SHARD / 2 + 1;
+// Static index: a shard holds 32766 targets and its postings are stored as the BYTE OFFSET of the target's counter
+// word (two 16-bit counters per word: offset = (local target & ~1) * 2 <= 65528); every k-mer has two sub-lists,
+// the even and the odd targets, each padded to a multiple of 8 entries with offset 65532 = word 16383, which no
+// target owns.  Turning a posting into its counter update then takes no arithmetic at all: the address is the
+// posting, the increment (1 or 0x10000) is a constant of the sub-list.
+constexpr int SHARD_STATIC = SHARD - 2;
+constexpr uint16_t POST_PAD = 65532;
 
 struct ShardDev {
   const uint32_t * start;  // 4^k + 1 list offsets (incremental index: where this shard's part of every list begins)
@@ -77,7 +84,7 @@ __device__ __forceinline__ bool kmer_at(const uint8_t * __restrict__ s, int p, i
 
 // ---- index build: pass 1 counts, pass 2 fills; one CTA per target, shared-memory bitmap dedupe ----
 template <bool FILL>
-__global__ void index_build_kernel(DevSeqs db, int t0, int nt, int k, int mask_lower,
+__global__ void index_build_kernel(DevSeqs db, int t0, int nt, int k, int mask_lower, int split,
                                    uint32_t * __restrict__ count /* pass1: counts; pass2: fill cursors */,
                                    const uint32_t * __restrict__ start, uint16_t * __restrict__ post)
 {
@@ -96,11 +103,12 @@ __global__ void index_build_kernel(DevSeqs db, int t0, int nt, int k, int mask_l
       uint32_t const bit = 1u << (km & 31);
       uint32_t const old = atomicOr(&bitmap[km >> 5], bit);
       if ((old & bit) == 0) {  // first occurrence in this target
+        uint32_t const list = split ? 2u * km + static_cast<uint32_t>(lt & 1) : km;   // static index: even / odd targets apart
         if (FILL) {
-          uint32_t const pos = atomicAdd(&count[km], 1u);
-          post[static_cast<size_t>(start[km]) + pos] = static_cast<uint16_t>(lt);
+          uint32_t const pos = atomicAdd(&count[list], 1u);
+          post[static_cast<size_t>(start[list]) + pos] = static_cast<uint16_t>((lt & ~1) << 1);
         } else {
-          atomicAdd(&count[km], 1u);
+          atomicAdd(&count[list], 1u);
         }
       }
     }
@@ -117,6 +125,54 @@ __global__ void fill_u16_kernel(uint16_t * __restrict__ p, size_t n, uint16_t v)
 {
   size_t const i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) { p[i] = v; }
+}
+
+// Order inside a list does not matter to the counts, only to the speed of the shared-memory atomics that apply it:
+// the ranker's warp turns a list into counter updates 32 postings at a time — lane L holds vector blk*32 + L of the
+// list and instruction j of a vector round updates posting 8*(blk*32 + L) + j of every lane.  Those 32 postings are a
+// "row"; a row whose postings fall into 32 different shared-memory banks (bank = bits 2..6 of the stored counter offset) is applied in one pass, one with collisions is replayed.  This kernel sorts every list
+// by bank and deals the sorted postings out down the rows' lanes, so that the members of one row lie a whole
+// list / 32 apart in bank order: a row only collides where a bank holds more than 1/32 of the list.
+constexpr int BANK_ORDER_CAP = 8192;   // longer lists (a k-mer in a quarter of the shard) are left as they are
+__global__ void __launch_bounds__(128)
+list_bank_order_kernel(const uint32_t * __restrict__ start, uint16_t * __restrict__ post, int nlists)
+{
+  __shared__ uint16_t src[BANK_ORDER_CAP];
+  __shared__ uint32_t hist[32], cursor[32];
+  for (int li = blockIdx.x; li < nlists; li += gridDim.x) {
+    uint32_t const b = start[li];
+    int const n = static_cast<int>(start[li + 1] - b);   // a multiple of 8
+    if (n <= 32 || n > BANK_ORDER_CAP) { continue; }      // uniform per block
+    uint16_t * const lp = post + b;
+    if (threadIdx.x < 32) { hist[threadIdx.x] = 0; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      uint16_t const x = lp[i];
+      src[i] = x;
+      atomicAdd(&hist[(x >> 2) & 31], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t const v = hist[threadIdx.x];
+      uint32_t incl = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t const o = __shfl_up_sync(0xffffffffu, incl, d); if (threadIdx.x >= d) { incl += o; } }
+      cursor[threadIdx.x] = incl - v;
+    }
+    __syncthreads();
+    int const nv = n >> 3, full = nv >> 5, rem = nv & 31;   // vectors; whole 32-vector blocks; lanes used in the last block
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      uint16_t const x = src[i];
+      int const si = static_cast<int>(atomicAdd(&cursor[(x >> 2) & 31], 1u));   // rank in bank order
+      // positions in the order (lane, block, posting of the vector)
+      int const vr = si >> 3, j = si & 7;
+      int lane, blk;
+      if (vr < rem * (full + 1)) { lane = vr / (full + 1); blk = vr % (full + 1); }
+      else { int const v2 = vr - rem * (full + 1); lane = rem + v2 / full; blk = v2 % full; }
+      lp[8 * (blk * 32 + lane) + j] = x;
+    }
+    __syncthreads();
+  }
 }
 
 // ---- bitonic sort helpers on shared memory (descending for keys, ascending for k-mers) ----------
@@ -279,16 +335,24 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
       for (int i = threadIdx.x; i < np2; i += blockDim.x) {
         uint32_t const km = kmers[i];
         uint32_t b = 0, n = 0;
-        if (km != 0xffffffffu) { b = S.start[km]; n = (INCR ? S.end[km] : S.start[km + 1]) - b; }
+        if (km != 0xffffffffu) {
+          if (INCR) { b = S.start[km]; n = S.end[km] - b; }
+          else {
+            // even sub-list [b, mid), odd sub-list [mid, end): lengths in vectors of 8, both in one word
+            b = S.start[2 * km];
+            uint32_t const mid = S.start[2 * km + 1], e = S.start[2 * km + 2];
+            n = ((mid - b) >> 3) | (((e - mid) >> 3) << 16);
+          }
+        }
         lbeg[i] = b; llen[i] = n;
       }
       __syncthreads();
       // 3. postings -> counters (targets within a list are distinct, lists collide -> shared-memory
       //    atomics).  Lists are 16-byte aligned and padded, so a lane pulls 8 targets per 128-bit
-      //    load.  A warp walks TWO lists at a time and issues up to three loads per lane and list
-      //    before it touches a counter: six independent HBM requests per lane hide the latency that a
-      //    one-list-at-a-time loop exposes once per list (the typical list is ~70 vectors long).
-      //    Padding entries land in the dummy word counters[SHARD/2].
+      //    load.  A warp walks the two sub-lists of a k-mer at a time and issues up to three loads per lane and
+      //    sub-list before it touches a counter: six independent HBM requests per lane hide the latency that a
+      //    one-list-at-a-time loop exposes once per list.  Padding entries land in counter word 16383, which
+      //    no target of a static shard owns.
       if constexpr (INCR) {
         // unpadded lists of 32-bit target numbers: one warp per list, coalesced loads
         for (int li = warp; li < np2; li += NWARPS) {
@@ -300,23 +364,23 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
           }
         }
       } else {
+        // a warp takes one k-mer at a time: list a = its even targets (increment 1), list b = its odd targets
+        // (increment 0x10000)
         auto pair_len = [&](int li) -> uint32_t {
-          uint32_t const na = llen[li] >> 3;
-          uint32_t const nb = (li + NWARPS < np2) ? (llen[li + NWARPS] >> 3) : 0u;
+          uint32_t const na = llen[li] & 0xffffu, nb = llen[li] >> 16;
           return na > nb ? na : nb;
         };
         // One register buffer of six vectors (three per list): as soon as a vector has been turned into
-        // counter updates its slot is refilled from the NEXT (list pair, offset), so six loads per lane
+        // counter updates its slot is refilled from the NEXT (k-mer, offset), so six loads per lane
         // stay in flight without a second buffer (48 data registers would not leave room in the 64
         // this kernel may use at two 512-thread CTAs per SM).
         struct ListPair { uint32_t na, nb; const uint4 * pa; const uint4 * pb; };
         auto bounds_of = [&](int li) -> ListPair {
-          int const l2 = li + NWARPS;
           ListPair lp;
-          lp.na = llen[li] >> 3;
-          lp.nb = (l2 < np2) ? (llen[l2] >> 3) : 0u;
+          lp.na = llen[li] & 0xffffu;
+          lp.nb = llen[li] >> 16;
           lp.pa = reinterpret_cast<const uint4 *>(S.post + lbeg[li]);
-          lp.pb = reinterpret_cast<const uint4 *>(S.post + (l2 < np2 ? lbeg[l2] : 0u));
+          lp.pb = lp.pa + lp.na;
           return lp;
         };
         int li = warp;
@@ -335,8 +399,19 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
         while (have) {
           int nli = li;
           uint32_t nbase = base + 96;
-          if (nbase >= pair_len(li)) { nli = li + 2 * NWARPS; nbase = 0; }
+          if (nbase >= pair_len(li)) { nli = li + NWARPS; nbase = 0; }
           bool const nhave = nli < np2;
+          if (nbase == 0) {
+            // the register buffer only reaches one k-mer ahead, less than a trip to HBM takes: pull the k-mer three
+            // turns ahead into L2 now (its two sub-lists are one contiguous run of 128-byte lines, one line per lane)
+            int const pli = nli + RANK_PREFETCH * NWARPS;
+            if (pli < np2) {
+              uint32_t const pn = (llen[pli] & 0xffffu) + (llen[pli] >> 16);   // vectors of 16 bytes
+              if (8u * lane < pn) {
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(S.post + lbeg[pli] + 64u * lane));
+              }
+            }
+          }
           ListPair lp{0u, 0u, nullptr, nullptr};
           if (nhave) { lp = bounds_of(nli); }
           uint32_t nvalid = 0;
@@ -344,11 +419,12 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
           for (int u = 0; u < 6; u++) {
             if ((valid & (1u << u)) != 0u) {
               uint32_t const w[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
+              uint32_t const inc = u < 3 ? 1u : 0x10000u;
 #pragma unroll
               for (int k = 0; k < 4; k++) {
-                uint32_t const a = w[k] & 0xffffu, b = w[k] >> 16;
-                atomicAdd(&counters[a >> 1], (a & 1) ? 0x10000u : 1u);
-                atomicAdd(&counters[b >> 1], (b & 1) ? 0x10000u : 1u);
+                uint32_t const a = w[k] & 0xffffu, b = w[k] >> 16;   // byte offsets of the counter words
+                atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(counters) + a), inc);
+                atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(counters) + b), inc);
               }
             }
             uint32_t const e = nbase + lane + 32u * (u % 3);
@@ -576,46 +652,55 @@ extern "C" int vsg_index_create(vsg_ctx * c, const vsg_seqset * db, int wordleng
     VSG_CUDA_OK(cudaFuncSetAttribute(index_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bitmap_bytes)));
     VSG_CUDA_OK(cudaFuncSetAttribute(index_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bitmap_bytes)));
   }
-  int const nshards = static_cast<int>((db->d.n + SHARD - 1) / SHARD);
+  int const nshards = static_cast<int>((db->d.n + SHARD_STATIC - 1) / SHARD_STATIC);
+  size_t const nlists = 2 * hashsize;   // even and odd targets of every k-mer
   ix->b_start.resize(static_cast<size_t>(nshards));
   ix->b_post.resize(static_cast<size_t>(nshards));
   DevBuf cnt, tmp;
   int rc;
-  if ((rc = cnt.reserve(sizeof(uint32_t) * (hashsize + 1))) != VSG_OK) { vsg_index_destroy(ix); return rc; }
+  if ((rc = cnt.reserve(sizeof(uint32_t) * (nlists + 1))) != VSG_OK) { vsg_index_destroy(ix); return rc; }
   for (int sh = 0; sh < nshards; sh++) {
-    int const t0 = sh * SHARD;
-    int const nt = static_cast<int>(std::min<int64_t>(SHARD, db->d.n - t0));
+    int const t0 = sh * SHARD_STATIC;
+    int const nt = static_cast<int>(std::min<int64_t>(SHARD_STATIC, db->d.n - t0));
     DevBuf & bs = ix->b_start[static_cast<size_t>(sh)];
-    if ((rc = bs.reserve(sizeof(uint32_t) * (hashsize + 1))) != VSG_OK) { vsg_index_destroy(ix); return rc; }
-    VSG_CUDA_OK(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * (hashsize + 1), c->stream));
-    index_build_kernel<false><<<nt, 128, bitmap_bytes, c->stream>>>(db->d, t0, nt, k, mask_lower,
+    if ((rc = bs.reserve(sizeof(uint32_t) * (nlists + 1))) != VSG_OK) { vsg_index_destroy(ix); return rc; }
+    VSG_CUDA_OK(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * (nlists + 1), c->stream));
+    index_build_kernel<false><<<nt, 128, bitmap_bytes, c->stream>>>(db->d, t0, nt, k, mask_lower, 1,
                                                                     static_cast<uint32_t *>(cnt.p), nullptr, nullptr);
     count_launch();
-    pad_counts_kernel<<<static_cast<unsigned>((hashsize + 255) / 256), 256, 0, c->stream>>>(static_cast<uint32_t *>(cnt.p), static_cast<int>(hashsize));
+    pad_counts_kernel<<<static_cast<unsigned>((nlists + 255) / 256), 256, 0, c->stream>>>(static_cast<uint32_t *>(cnt.p), static_cast<int>(nlists));
     count_launch();
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, static_cast<uint32_t *>(cnt.p), static_cast<uint32_t *>(bs.p),
-                                  static_cast<int>(hashsize + 1), c->stream);
+                                  static_cast<int>(nlists + 1), c->stream);
     if ((rc = tmp.reserve(tb + 16)) != VSG_OK) { vsg_index_destroy(ix); return rc; }
     cub::DeviceScan::ExclusiveSum(tmp.p, tb, static_cast<uint32_t *>(cnt.p), static_cast<uint32_t *>(bs.p),
-                                  static_cast<int>(hashsize + 1), c->stream);
+                                  static_cast<int>(nlists + 1), c->stream);
     count_launch();
     uint32_t total = 0;
-    VSG_CUDA_OK(cudaMemcpyAsync(&total, static_cast<uint32_t *>(bs.p) + hashsize, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    VSG_CUDA_OK(cudaMemcpyAsync(&total, static_cast<uint32_t *>(bs.p) + nlists, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
     DevBuf & bp = ix->b_post[static_cast<size_t>(sh)];
     if ((rc = bp.reserve(sizeof(uint16_t) * (static_cast<size_t>(total) + 64))) != VSG_OK) { vsg_index_destroy(ix); return rc; }
-    VSG_CUDA_OK(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * (hashsize + 1), c->stream));
+    VSG_CUDA_OK(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * (nlists + 1), c->stream));
     if (total > 0) {
       fill_u16_kernel<<<static_cast<unsigned>((static_cast<size_t>(total) + 255) / 256), 256, 0, c->stream>>>(
           static_cast<uint16_t *>(bp.p), static_cast<size_t>(total), POST_PAD);
       count_launch();
     }
-    index_build_kernel<true><<<nt, 128, bitmap_bytes, c->stream>>>(db->d, t0, nt, k, mask_lower,
+    index_build_kernel<true><<<nt, 128, bitmap_bytes, c->stream>>>(db->d, t0, nt, k, mask_lower, 1,
                                                                    static_cast<uint32_t *>(cnt.p),
                                                                    static_cast<uint32_t *>(bs.p),
                                                                    static_cast<uint16_t *>(bp.p));
     count_launch();
+    static bool const bank_order = [] { const char * e = std::getenv("VSG_BANK_ORDER"); return e == nullptr || e[0] != '0'; }();
+    if (total > 0 && bank_order) {
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+      list_bank_order_kernel<<<std::min<int>(static_cast<int>(nlists), sms * 32), 128, 0, c->stream>>>(
+          static_cast<const uint32_t *>(bs.p), static_cast<uint16_t *>(bp.p), static_cast<int>(nlists));
+      count_launch();
+    }
     ShardDev sd;
     sd.start = static_cast<uint32_t *>(bs.p); sd.post = static_cast<uint16_t *>(bp.p); sd.t0 = t0; sd.nt = nt;
     sd.end = nullptr; sd.post32 = nullptr;
@@ -803,7 +888,7 @@ int cindex_create(vsg_ctx * c, const vsg_seqset * set, int wordlength, int mask_
   int64_t const n = set->d.n;
   for (int64_t t0 = 0; t0 < n; t0 += 1 << 20) {
     int const nt = static_cast<int>(std::min<int64_t>(1 << 20, n - t0));
-    index_build_kernel<false><<<nt, 128, bitmap_bytes, c->stream>>>(set->d, static_cast<int>(t0), nt, wordlength, mask_lower,
+    index_build_kernel<false><<<nt, 128, bitmap_bytes, c->stream>>>(set->d, static_cast<int>(t0), nt, wordlength, mask_lower, 0,
                                                                     static_cast<uint32_t *>(cnt.p), nullptr, nullptr);
     count_launch();
   }
