@@ -600,13 +600,16 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
   ScoreParams const & sp = c->sp;
   FastBound const fbound = fast_bound_of(sp);
   FastBound const fbound2 = fast_bound_of(c->sp2);
-  // Small calls are latency-bound (the cluster driver's rounds, the tail rounds of a search): one thread
-  // regenerating ~40 tiles takes several hundred microseconds whatever the batch size, while walking stored
-  // direction bits takes tens.  Below VSG_CKPT_MIN_PAIRS pairs (default 2048) the direction-bit kernels are used;
-  // both paths are bit-identical (tests/test_stress_gpu.py runs either).
+  // Small calls are latency-bound (the cluster driver's rounds, the tail rounds of a search).  For sequences of
+  // similar length one thread regenerating ~40 tiles takes a few hundred microseconds whatever the batch size while
+  // walking stored direction bits takes tens: below VSG_CKPT_MIN_PAIRS pairs (default 2048) such pairs use the
+  // direction-bit kernels.  A target several times longer than the query turns that around — the walk over stored
+  // bits pays one dependent HBM load per column of the end gap, the regenerated tiles cross it 32 columns at a time
+  // — so those pairs stay on the checkpoint kernels at any call size.  Both paths are bit-identical
+  // (tests/test_stress_gpu.py runs either).
   const char * const ckpt_min_env = std::getenv("VSG_CKPT_MIN_PAIRS");   // read per call: tests switch it
   int64_t const ckpt_min_pairs = ckpt_min_env != nullptr ? std::atoll(ckpt_min_env) : 2048LL;
-  bool const use_ckpt = c->ckpt_enabled && npairs >= ckpt_min_pairs;
+  bool const ckpt_any_size = c->ckpt_enabled && npairs >= ckpt_min_pairs;
   std::vector<FastTask> all_fast;
   std::vector<ExactTask> all_exact;
   std::vector<PairDesc> all_pairs;  // CIGAR mode only
@@ -727,7 +730,7 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
         int const dmax = std::max(a.d, b.d);
         // single-strip tasks go through the checkpoint kernel (no direction bits; align_ckpt.cuh) when its
         // shifted scoring stays inside the exact range too
-        bool const ck = (ns == 1) && use_ckpt && fast_path_ok(fbound2, 32 * R, dmax);
+        bool const ck = (ns == 1) && c->ckpt_enabled && (ckpt_any_size || dmax >= 3 * Q) && fast_path_ok(fbound2, 32 * R, dmax);
         uint64_t const dirb = ck ? ck_row_elems(dmax) * sizeof(uint2) : static_cast<uint64_t>(ns) * fast_strip_bytes(dmax, R);
         uint64_t const auxe = ck ? ck_col_elems(dmax, R) : (ns > 1 ? static_cast<uint64_t>(dmax) : 0);
         if (!cb.empty() && cb.dir_bytes + dirb + (cb.bnd_elems + auxe) * sizeof(uint2) > c->dir_budget) { close_chunk(); }
