@@ -295,6 +295,21 @@ typedef struct vsg_cluster_result {
 int vsg_cluster_fast(vsg_ctx * ctx, const vsg_seqset * set, const vsg_search_opts * opts, int round_size,
                      vsg_cluster_result * results, int64_t * nclusters, int64_t * work);
 
+/* ---- the same clustering as a SESSION that is fed ranges of the set: replaces cluster_session_init /
+ *      cluster_assign_single / cluster_assign_batch / cluster_session_cleanup (core/cluster.hpp:78-118,
+ *      core/cluster.cpp:1633-1930).  The session owns the device index of the centroids found so far and the cluster
+ *      numbers; `set` (already masked and sorted, as for vsg_cluster_fast), the context and the arrays `opts` points
+ *      to must outlive it.  vsg_cluster_session_assign handles the sequences [start, start + count) in rounds of
+ *      round_size (cluster_assign_batch: the caller's --threads; cluster_assign_single: count = round_size = 1);
+ *      ranges must be ascending and contiguous (cluster.hpp:104-111), results[i] belongs to sequence start + i.
+ *      A session fed the whole set in one call gives vsg_cluster_fast's results. ---- */
+typedef struct vsg_cluster_session vsg_cluster_session;
+int vsg_cluster_session_create(vsg_ctx * ctx, const vsg_seqset * set, const vsg_search_opts * opts, vsg_cluster_session ** out);
+int vsg_cluster_session_assign(vsg_cluster_session * session, int64_t start, int64_t count, int round_size,
+                               vsg_cluster_result * results);
+int64_t vsg_cluster_session_clusters(const vsg_cluster_session * session);
+void vsg_cluster_session_destroy(vsg_cluster_session * session);
+
 /* ---- several GPUs behind one process (the reference is a single process, LIBRARY_API.md:138-156):
  *      vsg_group_create uploads the database ONCE (to devices[0]; dust_db != 0 also DUST-masks it there,
  *      core/mask.cpp dust_all), copies the packed sequences device to device over NVLink to every other GPU and

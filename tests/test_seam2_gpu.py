@@ -112,3 +112,60 @@ def test_search_batch_shim_equals_reference(tmp_path, case):
     assert outs[0] == outs[1], (len(outs[0]), len(outs[1]), [x for x in zip(outs[0], outs[1]) if x[0] != x[1]][:5])
     if "maxaccepts=0" not in case:
         assert len(outs[0]) > 5
+
+
+# ---- the clustering half of seam 2: cluster_session_* / cluster_assign_* (src/core/cluster.hpp:78-118) ----
+needs_cluster_ref = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "seam2_cluster_driver_gpu")),
+                                       reason="oracle/_ref (compiled reference + cluster shim) not present")
+
+
+@needs_cluster_ref
+def test_reference_example_cluster_runs_on_the_gpu_shims():
+    """the reference's own api_examples/example_cluster.cc, unmodified, against shim/cluster_session_vsg.cpp"""
+    cwd = os.path.join(REF, "api_data")
+    r = subprocess.run([os.path.join(REF, "example_cluster_gpu")], cwd=cwd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    want = sorted(l for l in open(os.path.join(cwd, "data", "expected_cluster.uc")).read().splitlines() if l[:1] in "SH")
+    got = sorted(l for l in r.stdout.splitlines() if l[:1] in "SH")
+    assert got == want and len(got) > 0
+    assert "PASS: batch cluster matches sequential" in r.stderr
+    assert "FAIL" not in r.stderr
+
+
+def _reads(tmp_path):
+    rng = np.random.default_rng(77)
+    roots = synth.random_seqs(rng, 40, 320)
+    recs = []
+    for i in range(1500):
+        m = synth.mutate(rng, roots[int(rng.integers(0, 40))], float(rng.uniform(0.0, 0.06))).tobytes()
+        a, b = int(rng.integers(0, 25)), int(rng.integers(0, 25))
+        s = m[a: len(m) - b]
+        if i % 41 == 7:
+            s = s[:100] + b"ACACACACACACACACACACACACACACACACACAC" + s[100:]   # DUST bait
+        if i % 97 == 11:
+            s = s[:50] + b"NRY" + s[53:]                                        # IUPAC -> the general kernel
+        recs.append([f"r{i}", s.decode()])
+    path = str(tmp_path / "reads.fasta")
+    _write_fasta(path, recs)
+    return path
+
+
+@needs_cluster_ref
+@pytest.mark.parametrize("case", [
+    ["id=0.97", "threads=1", "chunk=-1"],                      # cluster_assign_single, one by one
+    ["id=0.97", "threads=8", "chunk=0"],                       # one cluster_assign_batch over everything
+    ["id=0.95", "threads=32", "chunk=257", "maxrejects=16"],   # ranges that do not line up with the rounds
+    ["id=0.9", "threads=128", "chunk=700", "qmask=none", "maxaccepts=2", "iddef=1"],
+    ["id=0.97", "threads=4", "chunk=400", "minsl=0.9", "mid=0.9"],
+])
+def test_cluster_session_shim_equals_the_reference(tmp_path, case):
+    reads = _reads(tmp_path)
+    outs = []
+    for exe in ("seam2_cluster_driver_ref", "seam2_cluster_driver_gpu"):
+        r = subprocess.run([os.path.join(REF, exe), reads] + case, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, (exe, r.stdout[-2000:], r.stderr[-2000:])
+        outs.append(r.stdout.splitlines())
+    assert len(outs[0]) == 1500
+    assert outs[0] == outs[1]
+    ncent = sum(1 for l in outs[0] if l.split("\t")[2] == "1")
+    assert 30 <= ncent < 1500

@@ -80,19 +80,33 @@ unsigned shared_count(const std::vector<uint32_t> & a, const std::vector<uint64_
 
 }  // namespace
 
-extern "C" int vsg_cluster_fast(vsg_ctx * c, const vsg_seqset * set, const vsg_search_opts * opts, int round_size,
-                                vsg_cluster_result * results, int64_t * nclusters, int64_t * work)
+struct vsg_cluster_session {
+  vsg_ctx * c = nullptr;
+  const vsg_seqset * set = nullptr;
+  vsg_search_opts opts;
+  int64_t seqcount = 0, maxaccepts = 0, maxrejects = 0;
+  int tophits = 0, k = 0, minwordmatches = 0, hit_capacity = 0;
+  double opt_id = 0, opt_weak_id = 0;
+  vsg::CIndex * ix = nullptr;                      // the centroids indexed so far
+  int64_t total_pairs = 0, total_cells = 0, clusters = 0;
+  int64_t next = 0;                                // first sequence not assigned yet
+  std::vector<int32_t> cluster_of;                 // sequence -> cluster number (-1: not assigned yet)
+  std::vector<uint32_t> stamp;                     // distinct_kmers' scratch
+  uint32_t stamp_tag = 0;
+  ~vsg_cluster_session() { if (ix != nullptr) { cindex_destroy(ix); } }
+};
+
+namespace {
+
+// option checks and the clamps of cluster() (core/cluster.cpp:1213-1232); creates the (empty) incremental index
+int session_setup(vsg_ctx * c, const vsg_seqset * set, const vsg_search_opts * opts, vsg_cluster_session & s)
 {
-  if (c == nullptr || set == nullptr || opts == nullptr || results == nullptr || round_size < 1) { Error::set("vsg_cluster_fast: bad argument"); return VSG_EINVAL; }
   if (opts->strand_both != 0) { Error::set("vsg_cluster_fast: --strand both is not offered on this path"); return VSG_EINVAL; }
   if (opts->idprefix != 0 || opts->idsuffix != 0 || opts->selfid != 0) { Error::set("vsg_cluster_fast: idprefix/idsuffix/selfid are not offered on this path"); return VSG_EINVAL; }
   if (opts->iddef < 0 || opts->iddef > 4) { Error::set("vsg_cluster_fast: iddef must be 0..4"); return VSG_EINVAL; }
   if (opts->self != 0 && opts->target_labels == nullptr) { Error::set("vsg_cluster_fast: --self needs target_labels (one per sequence)"); return VSG_EINVAL; }
   VSG_CUDA_OK(cudaSetDevice(c->device));
   int64_t const seqcount = set->d.n;
-  if (nclusters != nullptr) { *nclusters = 0; }
-  if (work != nullptr) { work[0] = work[1] = 0; }
-  if (seqcount == 0) { return VSG_OK; }
   if (seqcount > 0x7fffffff) { Error::set("vsg_cluster_fast: too many sequences"); return VSG_EINVAL; }
   // the clamps of cluster() (core/cluster.cpp:1213-1232)
   int64_t maxaccepts = opts->maxaccepts, maxrejects = opts->maxrejects < 0 ? 32 : opts->maxrejects;
@@ -109,19 +123,38 @@ extern "C" int vsg_cluster_fast(vsg_ctx * c, const vsg_seqset * set, const vsg_s
   double const opt_weak_id = (opts->id >= 0.0 && opts->weak_id > opts->id) ? opts->id : opts->weak_id;
   int const hit_capacity = static_cast<int>(std::min<int64_t>(maxaccepts + maxrejects - 1, tophits));   // cluster.cpp:616-618
 
-  CIndex * ix = nullptr;
-  int rc = cindex_create(c, set, k, opts->mask_lower, &ix);
-  if (rc != VSG_OK) { return rc; }
-  struct Guard { CIndex * ix; ~Guard() { cindex_destroy(ix); } } guard{ix};
+  s.c = c; s.set = set; s.opts = *opts;
+  s.seqcount = seqcount; s.maxaccepts = maxaccepts; s.maxrejects = maxrejects;
+  s.tophits = tophits; s.k = k; s.minwordmatches = minwordmatches; s.hit_capacity = hit_capacity;
+  s.opt_id = opt_id; s.opt_weak_id = opt_weak_id;
+  s.cluster_of.assign(static_cast<size_t>(seqcount), -1);
+  s.stamp.assign(static_cast<size_t>(1) << (2 * k), 0u);
+  if (seqcount == 0) { return VSG_OK; }
+  return cindex_create(c, set, k, opts->mask_lower, &s.ix);
+}
 
+// cluster_core_parallel's rounds (core/cluster.cpp:877-1115) over the sequences [start, start + count); results[i] belongs
+// to sequence start + i.  State that outlives the call (index, cluster numbers) lives in the session.
+int session_rounds(vsg_cluster_session & s, int64_t const start, int64_t const count, int const round_size, vsg_cluster_result * results)
+{
+  vsg_ctx * const c = s.c;
+  const vsg_seqset * const set = s.set;
+  const vsg_search_opts * const opts = &s.opts;
+  int64_t const maxaccepts = s.maxaccepts, maxrejects = s.maxrejects;
+  int const tophits = s.tophits, k = s.k, minwordmatches = s.minwordmatches, hit_capacity = s.hit_capacity;
+  double const opt_id = s.opt_id, opt_weak_id = s.opt_weak_id;
+  CIndex * const ix = s.ix;
+  int64_t & total_pairs = s.total_pairs; int64_t & total_cells = s.total_cells; int64_t & clusters = s.clusters;
+  std::vector<int32_t> & cluster_of = s.cluster_of;
+  std::vector<uint32_t> & stamp = s.stamp;
+  uint32_t & stamp_tag = s.stamp_tag;
+  int rc = VSG_OK;
   auto size_of = [&](int seqno) -> int64_t { return opts->target_sizes != nullptr ? opts->target_sizes[seqno] : 1; };
   auto unaligned_ok = [&](int q, int qlen, int target) -> bool {
     bool const same_label = opts->self != 0 && opts->target_labels[q] == opts->target_labels[target];
     return acceptable_unaligned(*opts, qlen, set->h_len[static_cast<size_t>(target)], size_of(q), size_of(target), same_label, 0u);
   };
 
-  int64_t total_pairs = 0, total_cells = 0, clusters = 0;
-  std::vector<int32_t> cluster_of(static_cast<size_t>(seqcount), -1);
   std::vector<CQuery> rq(static_cast<size_t>(round_size));
   std::vector<uint32_t> h_seqno, h_count;
   std::vector<int32_t> h_n;
@@ -131,8 +164,6 @@ extern "C" int vsg_cluster_fast(vsg_ctx * c, const vsg_seqset * set, const vsg_s
   std::vector<uint8_t> round_sym;
   std::vector<uint32_t> new_centroids;
   const std::vector<uint32_t> & dense_to_seqno = cindex_seqnos(ix);
-  std::vector<uint32_t> stamp(static_cast<size_t>(1) << (2 * k), 0u);
-  uint32_t stamp_tag = 0;
 
   // the statistics search16 returned for one (query, target) -> struct hit (searchcore.cpp:842-857 / cluster.cpp:786-809)
   auto fill_hit = [&](Hit & h, int qlen, int16_t sc, uint16_t al, uint16_t ma, uint16_t mi, uint16_t ga, const int32_t * tr,
@@ -169,8 +200,8 @@ extern "C" int vsg_cluster_fast(vsg_ctx * c, const vsg_seqset * set, const vsg_s
   auto now = []() { return std::chrono::steady_clock::now(); };
   auto ms_since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
   double t_rank = 0, t_groups = 0, t_spec = 0, t_serial = 0, t_append = 0;
-  for (int64_t round0 = 0; round0 < seqcount; round0 += round_size) {
-    int const nqr = static_cast<int>(std::min<int64_t>(round_size, seqcount - round0));
+  for (int64_t round0 = start; round0 < start + count; round0 += round_size) {
+    int const nqr = static_cast<int>(std::min<int64_t>(round_size, start + count - round0));
     auto tp = now();
     // ---- 1a. candidate ranking of the whole round against the centroids indexed so far ----
     size_t const cells = static_cast<size_t>(nqr) * tophits;
@@ -419,7 +450,7 @@ extern "C" int vsg_cluster_fast(vsg_ctx * c, const vsg_seqset * set, const vsg_s
       const Hit * best = nullptr;
       for (const Hit & h : S.hits) { if (best == nullptr || hit_less(h, *best)) { best = &h; } }
       if (best != nullptr && !best->accepted) { best = nullptr; }
-      vsg_cluster_result & r = results[static_cast<size_t>(S.seqno)];
+      vsg_cluster_result & r = results[static_cast<size_t>(S.seqno - start)];
       std::memset(&r, 0, sizeof r);
       if (best != nullptr) {
         r.cluster = cluster_of[static_cast<size_t>(best->target)];
@@ -444,11 +475,61 @@ extern "C" int vsg_cluster_fast(vsg_ctx * c, const vsg_seqset * set, const vsg_s
     t_append += ms_since(tp);
   }
   if (trace) {
-    std::fprintf(stderr, "[vsg trace] cluster_fast %lld sequences, round %d: rank %.0f ms, candidate groups %.0f ms, speculative extras %.0f ms, "
-                 "serial pass %.0f ms, index append %.0f ms; %lld pairs\n", static_cast<long long>(seqcount), round_size, t_rank, t_groups,
-                 t_spec, t_serial, t_append, static_cast<long long>(total_pairs));
+    std::fprintf(stderr, "[vsg trace] cluster rounds %lld..%lld, round %d: rank %.0f ms, candidate groups %.0f ms, speculative extras %.0f ms, "
+                 "serial pass %.0f ms, index append %.0f ms; %lld pairs so far\n", static_cast<long long>(start), static_cast<long long>(start + count),
+                 round_size, t_rank, t_groups, t_spec, t_serial, t_append, static_cast<long long>(total_pairs));
   }
-  if (nclusters != nullptr) { *nclusters = clusters; }
-  if (work != nullptr) { work[0] = total_pairs; work[1] = total_cells; }
+  s.next = start + count;
   return VSG_OK;
+}
+
+}  // namespace
+
+extern "C" int vsg_cluster_fast(vsg_ctx * c, const vsg_seqset * set, const vsg_search_opts * opts, int round_size,
+                                vsg_cluster_result * results, int64_t * nclusters, int64_t * work)
+{
+  if (c == nullptr || set == nullptr || opts == nullptr || results == nullptr || round_size < 1) { Error::set("vsg_cluster_fast: bad argument"); return VSG_EINVAL; }
+  if (nclusters != nullptr) { *nclusters = 0; }
+  if (work != nullptr) { work[0] = work[1] = 0; }
+  vsg_cluster_session s;
+  int rc = session_setup(c, set, opts, s);
+  if (rc != VSG_OK || s.seqcount == 0) { return rc; }
+  if ((rc = session_rounds(s, 0, s.seqcount, round_size, results)) != VSG_OK) { return rc; }
+  if (nclusters != nullptr) { *nclusters = s.clusters; }
+  if (work != nullptr) { work[0] = s.total_pairs; work[1] = s.total_cells; }
+  return VSG_OK;
+}
+
+// ---- the incremental form: cluster_session_init / cluster_assign_single / cluster_assign_batch (core/cluster.hpp:78-118) ----
+extern "C" int vsg_cluster_session_create(vsg_ctx * c, const vsg_seqset * set, const vsg_search_opts * opts, vsg_cluster_session ** out)
+{
+  if (c == nullptr || set == nullptr || opts == nullptr || out == nullptr) { Error::set("vsg_cluster_session_create: null argument"); return VSG_EINVAL; }
+  *out = nullptr;
+  vsg_cluster_session * s = new (std::nothrow) vsg_cluster_session();
+  if (s == nullptr) { Error::set("out of host memory"); return VSG_ENOMEM; }
+  int const rc = session_setup(c, set, opts, *s);
+  if (rc != VSG_OK) { delete s; return rc; }
+  *out = s;
+  return VSG_OK;
+}
+
+extern "C" int vsg_cluster_session_assign(vsg_cluster_session * s, int64_t start, int64_t count, int round_size, vsg_cluster_result * results)
+{
+  if (s == nullptr || results == nullptr || round_size < 1 || count < 0) { Error::set("vsg_cluster_session_assign: bad argument"); return VSG_EINVAL; }
+  if (start != s->next || start + count > s->seqcount) {
+    Error::set("vsg_cluster_session_assign: ranges must be ascending, contiguous and inside the set (cluster.hpp:104-111)");
+    return VSG_EINVAL;
+  }
+  if (count == 0) { return VSG_OK; }
+  VSG_CUDA_OK(cudaSetDevice(s->c->device));
+  return session_rounds(*s, start, count, round_size, results);
+}
+
+extern "C" int64_t vsg_cluster_session_clusters(const vsg_cluster_session * s) { return s != nullptr ? s->clusters : 0; }
+
+extern "C" void vsg_cluster_session_destroy(vsg_cluster_session * s)
+{
+  if (s == nullptr) { return; }
+  cudaSetDevice(s->c->device);
+  delete s;
 }

@@ -323,6 +323,37 @@ def cluster_fast(ctx: "Context", ss: SeqSetHandle, opts: SearchOpts, round_size:
     return res, int(ncl.value), work
 
 
+_CLUSTER_DT = np.dtype([("cluster", np.int32), ("centroid", np.int32), ("matches", np.int32), ("mismatches", np.int32),
+                        ("gaps", np.int32), ("alignment_length", np.int32), ("nwscore", np.int32), ("strand", np.int32),
+                        ("id", np.float64)])
+
+
+class ClusterSession:
+    """vsg_cluster_session: the clustering fed range by range (cluster_assign_batch / cluster_assign_single)"""
+
+    def __init__(self, ctx: "Context", ss: SeqSetHandle, opts: SearchOpts):
+        self._keep = (ctx, ss, opts)
+        self.h = C.c_void_p()
+        lib = load()
+        lib.vsg_cluster_session_clusters.restype = C.c_int64
+        _check(lib.vsg_cluster_session_create(ctx.h, ss.h, C.byref(opts), C.byref(self.h)), "vsg_cluster_session_create")
+
+    def assign(self, start: int, count: int, round_size: int):
+        res = np.zeros(count, dtype=_CLUSTER_DT)
+        _check(load().vsg_cluster_session_assign(self.h, C.c_int64(start), C.c_int64(count), C.c_int(round_size),
+                                                 res.ctypes.data_as(C.POINTER(ClusterResult))), "vsg_cluster_session_assign")
+        return res
+
+    @property
+    def clusters(self) -> int:
+        return int(load().vsg_cluster_session_clusters(self.h))
+
+    def close(self):
+        if self.h:
+            load().vsg_cluster_session_destroy(self.h)
+            self.h = C.c_void_p()
+
+
 class Group:
     """vsg_group: one process, several GPUs (database copied device to device, queries / rows sharded)"""
 
