@@ -227,6 +227,8 @@ typedef struct vsg_search_result {
   int32_t strand;
   int32_t nwscore;
   double id;
+  int32_t internal_alignment_length;   /* alignment columns / gap opens without the terminal gaps that align_trim   */
+  int32_t internal_gaps;               /* removes (core/searchcore.cpp:409-463): the --blast6out columns 4 and 6     */
 } vsg_search_result;
 
 void vsg_search_opts_default(vsg_search_opts * o);
@@ -335,6 +337,23 @@ int vsg_group_search(vsg_group * g, const char * qcat, const int64_t * qoff, con
                      int32_t * counts, int64_t * work);
 int vsg_group_allpairs(vsg_group * g, const vsg_search_opts * opts, vsg_pair_hit * hits, int64_t cap,
                        int64_t * nhits, int64_t * work);
+
+/* ---- streaming --usearch_global driver: replaces the query loop of search_thread_run /
+ *      search_output_results (commands/usearch_global.cpp:150-300, 376-534) for FASTA in, --blast6out out
+ *      (core/results.cpp:221-271).  Three stages run concurrently on batches of batch_queries sequences:
+ *      a reader thread parses the FASTA file (headers cut at the first blank unless notrunclabels), the calling
+ *      thread runs vsg_group_search on every GPU of the group (query upload, optional DUST, ranking, alignment,
+ *      accept/reject, hit table download), a writer thread formats the rows of min(maxhits, hits) per query IN INPUT
+ *      ORDER (the reference's order with --threads 1).  target_labels: the database headers as the reference would
+ *      print them.  output_no_hits != 0: the "*" row for queries without a hit.  stats (optional) receives counts and
+ *      the busy seconds of each stage. ---- */
+typedef struct vsg_stream_stats {
+  int64_t queries, matched, rows, batches, nucleotides;
+  double parse_s, search_s, write_s, wall_s;
+} vsg_stream_stats;
+int vsg_usearch_stream(vsg_group * g, const char * const * target_labels, const char * query_fasta,
+                       const vsg_search_opts * opts, int qmask_dust, int notrunclabels, int batch_queries,
+                       int64_t maxhits, int output_no_hits, const char * blast6out_path, vsg_stream_stats * stats);
 
 #ifdef __cplusplus
 }

@@ -574,6 +574,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
         r.query_length = queries->h_len[static_cast<size_t>(q0 + b0 + q)];
         r.target_length = db->h_len[static_cast<size_t>(h.target)];
         r.accepted = h.accepted ? 1 : 0; r.strand = h.strand; r.nwscore = h.nwscore; r.id = h.id;
+        r.internal_alignment_length = h.internal_alignmentlength; r.internal_gaps = h.internal_gaps;
       }
       counts[b0 + q] = n;
     }

@@ -57,7 +57,8 @@ class SearchResult(C.Structure):
     _fields_ = [("target", C.c_int32), ("matches", C.c_int32), ("mismatches", C.c_int32),
                 ("gaps", C.c_int32), ("alignment_length", C.c_int32), ("query_length", C.c_int32),
                 ("target_length", C.c_int32), ("accepted", C.c_int32), ("strand", C.c_int32),
-                ("nwscore", C.c_int32), ("id", C.c_double)]
+                ("nwscore", C.c_int32), ("id", C.c_double),
+                ("internal_alignment_length", C.c_int32), ("internal_gaps", C.c_int32)]
 
 
 class PairHit(C.Structure):
@@ -407,6 +408,21 @@ class Group:
         _check(load().vsg_group_allpairs(self.h, C.byref(opts), hits.ctypes.data_as(C.POINTER(PairHit)), C.c_int64(cap),
                                          C.byref(n), _ptr(work, C.c_int64)), "vsg_group_allpairs")
         return hits[: n.value], work
+
+    def stream(self, target_labels, query_fasta: str, opts: SearchOpts, blast6out: str, qmask_dust: int = 0, notrunclabels: int = 0,
+               batch_queries: int = 65536, maxhits: int = 0, output_no_hits: int = 0):
+        """vsg_usearch_stream: FASTA file in, --blast6out file out; returns the statistics record as a dict"""
+        labs = (C.c_char_p * len(target_labels))(*[l if isinstance(l, bytes) else l.encode() for l in target_labels])
+        st = StreamStats()
+        _check(load().vsg_usearch_stream(self.h, labs, query_fasta.encode(), C.byref(opts), C.c_int(qmask_dust), C.c_int(notrunclabels),
+                                         C.c_int(batch_queries), C.c_int64(maxhits), C.c_int(output_no_hits), blast6out.encode(),
+                                         C.byref(st)), "vsg_usearch_stream")
+        return {k: getattr(st, k) for k, _ in StreamStats._fields_}
+
+
+class StreamStats(C.Structure):
+    _fields_ = [("queries", C.c_int64), ("matched", C.c_int64), ("rows", C.c_int64), ("batches", C.c_int64), ("nucleotides", C.c_int64),
+                ("parse_s", C.c_double), ("search_s", C.c_double), ("write_s", C.c_double), ("wall_s", C.c_double)]
 
 
 def default_search_opts() -> SearchOpts:
