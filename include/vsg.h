@@ -152,6 +152,10 @@ int vsg_measure_int_peak(vsg_ctx * ctx, double * packed_lane_ops_per_s);
 int vsg_index_create(vsg_ctx * ctx, const vsg_seqset * db, int wordlength, int mask_lower,
                      vsg_index ** out);
 void vsg_index_destroy(vsg_index * ix);
+/* wordlength 3..15, as the reference (cli.cc --wordlength).  3..10: list heads for all 4^k words per shard of 32 766
+ * targets, targets de-duplicated through a bitmap (unique_count_bitmap, core/unique.cpp:155-240).  11..15: only the
+ * words that occur get a list, found by sorting (what unique_count_hash's table finds, core/unique.cpp:243-334),
+ * looked up by binary search. */
 
 /* ---- candidate ranking: replaces unique_count + search_topscores + minheap
  *      (core/unique.cpp:337-353, core/searchcore.cpp:260-340, core/minheap.cpp) for every query
@@ -354,6 +358,31 @@ typedef struct vsg_stream_stats {
 int vsg_usearch_stream(vsg_group * g, const char * const * target_labels, const char * query_fasta,
                        const vsg_search_opts * opts, int qmask_dust, int notrunclabels, int batch_queries,
                        int64_t maxhits, int output_no_hits, const char * blast6out_path, vsg_stream_stats * stats);
+
+/* ---- UDB database files: replaces udb_detect_isudb and udb_read (core/udb.cpp:120-175, 196-578).
+ *      vsg_udb_detect: 1 if the file starts with the UDB signature, 0 if not, < 0 on error.  vsg_udb_open parses and
+ *      validates the whole file on the host (no GPU needed; every "Invalid UDB file" check of udb_read, as VSG_EINVAL);
+ *      the accessors hand out views that live until vsg_udb_close: the sequences (ASCII, back to back; case carries
+ *      the masking the file was made with), the NUL-terminated headers, the stored word index (kmercount[4^k], then
+ *      the ascending sequence numbers of every word).  vsg_udb_load makes the device-resident database: sequences
+ *      uploaded, the device index built at the file's word length and CHECKED against the stored one (per word, the
+ *      number of sequences holding it); *mask_lower (optional) receives whether the stored index excludes lower-case
+ *      symbols (--dbmask dust/soft when the file was made) — pass it on as the index's masking.  A file whose stored
+ *      counts match neither convention is rejected.  vsg_group_create_udb: the same for a vsg_group. ---- */
+typedef struct vsg_udb vsg_udb;
+typedef struct vsg_udb_info {
+  int64_t sequences, nucleotides, header_chars, index_entries, longest_header;
+  int32_t wordlength, dbaccel, shortest, longest;
+} vsg_udb_info;
+int vsg_udb_detect(const char * path);
+int vsg_udb_open(const char * path, vsg_udb ** out);
+void vsg_udb_close(vsg_udb * udb);
+int vsg_udb_info_get(const vsg_udb * udb, vsg_udb_info * out);
+int vsg_udb_sequences(const vsg_udb * udb, const char ** cat, const int64_t ** off, const int32_t ** len);
+const char * vsg_udb_header(const vsg_udb * udb, int64_t i);
+int vsg_udb_words(const vsg_udb * udb, const uint32_t ** kmercount, const uint32_t ** kmerindex);
+int vsg_udb_load(vsg_ctx * ctx, const vsg_udb * udb, vsg_seqset ** db, vsg_index ** index, int * mask_lower);
+int vsg_group_create_udb(const int * devices, int ndev, const vsg_scoring * scoring, const vsg_udb * udb, vsg_group ** out);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,8 @@ unsigned int oracle_unique_kmers(int k, const char * seq, int64_t len, int mask_
 typedef struct oracle_index oracle_index; /* CSR postings over 4^k k-mers */
 oracle_index * oracle_index_build(int k, int n, const char * cat, const int64_t * off,
                                   const int * len, int mask_lower);
+void oracle_index_starts(const oracle_index * ix, uint64_t * start);
+void oracle_index_postings(const oracle_index * ix, uint32_t * post);
 void oracle_index_free(oracle_index * ix);
 
 /* search_topscores: best-first (count desc, length asc, seqno asc) list of at most

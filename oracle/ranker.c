@@ -24,8 +24,40 @@
 #include <stdio.h>
 #include <math.h>
 
+/* k >= 10: the reference switches from the 4^k-bit map to an open-addressing table of 2 * seqlen buckets keyed by the
+ * k-mer itself (unique_count_hash, unique.cpp:243-334).  The bucket a k-mer lands in (CityHash there, a
+ * multiplicative hash here) decides nothing: a k-mer is reported the first time it is seen, in sequence order. */
+static unsigned int unique_kmers_hash(int k, const char * seq, int64_t len, int mask_lower, uint32_t * out)
+{
+  uint64_t const mask = (1ULL << (2 * k)) - 1ULL;
+  uint64_t size = 1;
+  while (size < (uint64_t)(2 * len) || size < 2) { size *= 2; }
+  uint32_t * tab = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)size);
+  if (!tab) { abort(); }
+  memset(tab, 0xff, sizeof(uint32_t) * (size_t)size); /* 0xffffffff = empty (a k-mer has at most 30 bits) */
+  uint64_t bad = 0, kmer = 0;
+  unsigned int unique = 0;
+  for (int64_t p = 0; p < len; p++) {
+    unsigned char const c = (unsigned char)seq[p];
+    bad = (bad << 2) | (mask_lower ? oracle_map_mask_lower(c) : oracle_map_mask_ambig(c));
+    kmer = (kmer << 2) | oracle_map_2bit(c);
+    if (p >= k - 1) {
+      bad &= mask;
+      kmer &= mask;
+      if (bad == 0) {
+        uint64_t j = ((uint32_t)kmer * 2654435761u) & (size - 1);
+        while (tab[j] != 0xffffffffu && tab[j] != (uint32_t)kmer) { j = (j + 1) & (size - 1); }
+        if (tab[j] == 0xffffffffu) { tab[j] = (uint32_t)kmer; out[unique++] = (uint32_t)kmer; }
+      }
+    }
+  }
+  free(tab);
+  return unique;
+}
+
 unsigned int oracle_unique_kmers(int k, const char * seq, int64_t len, int mask_lower, uint32_t * out)
 {
+  if (k >= 10) { return unique_kmers_hash(k, seq, len, mask_lower, out); } /* unique.cpp:337-353 */
   uint64_t const size = 1ULL << (2 * k);
   uint64_t const mask = size - 1ULL;
   uint8_t * seen = (uint8_t *)calloc((size_t)(size >> 3) + 1, 1);
@@ -52,9 +84,18 @@ unsigned int oracle_unique_kmers(int k, const char * seq, int64_t len, int mask_
 struct oracle_index {
   int k;
   int n;            /* indexed sequences; index number == seqno (add_all_sequences order) */
-  uint64_t * start; /* 4^k + 1 */
+  uint64_t * start; /* k <= 12: 4^k + 1 list heads.  k >= 13 (4^k heads would take gigabytes; the reference pays that,
+                       dbindex.cpp:163-182, a test helper need not): nkeys + 1 heads of the k-mers that occur */
+  uint32_t * keys;  /* k >= 13: those k-mers, ascending; NULL otherwise */
+  uint64_t nkeys;
   uint32_t * post;  /* ascending target numbers per k-mer */
 };
+
+static int pair_cmp(const void * a, const void * b)
+{
+  uint64_t const x = *(uint64_t const *)a, y = *(uint64_t const *)b;
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
 
 oracle_index * oracle_index_build(int k, int n, const char * cat, const int64_t * off,
                                   const int * len, int mask_lower)
@@ -62,10 +103,33 @@ oracle_index * oracle_index_build(int k, int n, const char * cat, const int64_t 
   oracle_index * ix = (oracle_index *)calloc(1, sizeof *ix);
   uint64_t const size = 1ULL << (2 * k);
   ix->k = k; ix->n = n;
-  ix->start = (uint64_t *)calloc((size_t)size + 1, sizeof(uint64_t));
   int maxlen = 1;
   for (int t = 0; t < n; t++) { if (len[t] > maxlen) { maxlen = len[t]; } }
   uint32_t * tmp = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)maxlen);
+  if (k >= 13) {
+    /* same postings, found by sorting (k-mer, target) pairs */
+    uint64_t total = 0;
+    for (int t = 0; t < n; t++) { total += oracle_unique_kmers(k, cat + off[t], len[t], mask_lower, tmp); }
+    uint64_t * pairs = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(total + 1));
+    uint64_t m = 0;
+    for (int t = 0; t < n; t++) {
+      unsigned int const u = oracle_unique_kmers(k, cat + off[t], len[t], mask_lower, tmp);
+      for (unsigned int i = 0; i < u; i++) { pairs[m++] = ((uint64_t)tmp[i] << 32) | (uint32_t)t; }
+    }
+    qsort(pairs, (size_t)m, sizeof(uint64_t), pair_cmp);
+    ix->keys = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(m + 1));
+    ix->start = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(m + 2));
+    ix->post = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(m + 1));
+    for (uint64_t i = 0; i < m; i++) {
+      uint32_t const km = (uint32_t)(pairs[i] >> 32);
+      if (ix->nkeys == 0 || ix->keys[ix->nkeys - 1] != km) { ix->keys[ix->nkeys] = km; ix->start[ix->nkeys] = i; ix->nkeys++; }
+      ix->post[i] = (uint32_t)pairs[i];
+    }
+    ix->start[ix->nkeys] = m;
+    free(pairs); free(tmp);
+    return ix;
+  }
+  ix->start = (uint64_t *)calloc((size_t)size + 1, sizeof(uint64_t));
   for (int t = 0; t < n; t++) { /* counting pass (dbindex.cpp:184-200) */
     unsigned int const u = oracle_unique_kmers(k, cat + off[t], len[t], mask_lower, tmp);
     for (unsigned int i = 0; i < u; i++) { ix->start[tmp[i] + 1]++; }
@@ -82,9 +146,34 @@ oracle_index * oracle_index_build(int k, int n, const char * cat, const int64_t 
   return ix;
 }
 
+/* list of k-mer km: [*a, *b) in ix->post */
+static void oracle_list(const oracle_index * ix, uint32_t km, uint64_t * a, uint64_t * b)
+{
+  if (ix->keys == NULL) { *a = ix->start[km]; *b = ix->start[km + 1]; return; }
+  uint64_t lo = 0, hi = ix->nkeys;
+  while (lo < hi) { uint64_t const mid = (lo + hi) >> 1; if (ix->keys[mid] < km) { lo = mid + 1; } else { hi = mid; } }
+  if (lo < ix->nkeys && ix->keys[lo] == km) { *a = ix->start[lo]; *b = ix->start[lo + 1]; } else { *a = *b = 0; }
+}
+
+/* the index as plain arrays (tests compare a UDB file's stored word index with it, udb.cpp:296-350):
+ * start has 4^k + 1 entries; post has start[4^k] entries, ascending target numbers per word */
+void oracle_index_starts(const oracle_index * ix, uint64_t * start)
+{
+  uint64_t const size = 1ULL << (2 * ix->k);
+  for (uint64_t km = 0; km < size; km++) { uint64_t a, b; oracle_list(ix, (uint32_t)km, &a, &b); start[km + 1] = b - a; }
+  start[0] = 0;
+  for (uint64_t km = 0; km < size; km++) { start[km + 1] += start[km]; }
+}
+
+void oracle_index_postings(const oracle_index * ix, uint32_t * post)
+{
+  uint64_t const total = ix->keys ? ix->start[ix->nkeys] : ix->start[(size_t)1 << (2 * ix->k)];
+  memcpy(post, ix->post, sizeof(uint32_t) * (size_t)total);
+}
+
 void oracle_index_free(oracle_index * ix)
 {
-  if (ix) { free(ix->start); free(ix->post); free(ix); }
+  if (ix) { free(ix->start); free(ix->keys); free(ix->post); free(ix); }
 }
 
 typedef struct { uint32_t count, seqno, length; } elem;
@@ -106,7 +195,8 @@ int oracle_topscores(const oracle_index * ix, const int * target_len,
 {
   uint16_t * cnt = (uint16_t *)calloc((size_t)ix->n + 1, sizeof(uint16_t));
   for (unsigned int i = 0; i < nkmers; i++) {
-    uint64_t const a = ix->start[kmers[i]], b = ix->start[kmers[i] + 1];
+    uint64_t a, b;
+    oracle_list(ix, kmers[i], &a, &b);
     for (uint64_t p = a; p < b; p++) {
       uint16_t * c = &cnt[ix->post[p]];
       if (*c < 32767) { (*c)++; } /* saturate at INT16_MAX (searchcore.cpp:306-315) */

@@ -5,11 +5,12 @@ import numpy as np
 from vsearch_b200 import lib as vlib, synth
 
 NQ = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
-dbm = synth.config2_db(100_000, 1500, 2024)
+C4 = "--c4" in sys.argv   # configs[3] shape: 1M x 1200 DB (31 shards), 150-nt queries
+dbm = synth.config2_db(1_000_000, 1200, 4) if C4 else synth.config2_db(100_000, 1500, 2024)
 ctx = vlib.Context(0)
 db = ctx.seqset(synth.SeqSet.from_matrix(dbm))
 t0 = time.time(); ix = ctx.index(db, 8, 0); print(f"index build {1e3*(time.time()-t0):.0f} ms")
-qs_h, _ = synth.config2_query_batch(dbm, NQ, batch=1)
+qs_h, _ = synth.config2_query_batch(dbm, NQ, 150, 0.10, batch=1) if C4 else synth.config2_query_batch(dbm, NQ, batch=1)
 qs = ctx.seqset(qs_h)
 for rep in range(3):
     ctx.profile_reset(); t0 = time.time()

@@ -20,6 +20,7 @@
 #include "vsg_internal.h"
 
 #include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -53,6 +54,11 @@ struct ShardDev {
   // list km is post32[start[km] .. end[km])
   const uint32_t * end;
   const uint32_t * post32;
+  // sparse static index (--wordlength 11..15): the sorted (k-mer << 1 | target parity) keys of the sub-lists that
+  // exist in this shard; sub-list i is post[start[i] .. start[i + 1]).  nr == 0: dense (start indexed by 2 * k-mer)
+  const uint32_t * rkeys;
+  uint32_t nr;
+  uint32_t reserved;
 };
 
 __device__ __forceinline__ bool sym_bad(int s, int mask_lower)
@@ -125,6 +131,55 @@ __global__ void fill_u16_kernel(uint16_t * __restrict__ p, size_t n, uint16_t v)
 {
   size_t const i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) { p[i] = v; }
+}
+
+// per-k-mer totals over the shards built so far (vsg_udb_load checks them against the file's word counts)
+__global__ void add_totals_kernel(const uint32_t * __restrict__ count /* 2 per k-mer */, uint32_t * __restrict__ totals, size_t hashsize)
+{
+  size_t const i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < hashsize) { totals[i] += count[2 * i] + count[2 * i + 1]; }
+}
+
+// ---- sparse build (--wordlength 11..15: 4^k list heads per shard would dwarf the postings) --------------------------
+// One 46-bit key per window: k-mer (30 bits) | target parity | local target >> 1 (14 bits); windows that hold a masked
+// symbol, and the first k-1 positions of a target, get SPARSE_INVALID, which sorts behind every real key.  Sorting the
+// keys and dropping duplicates IS the per-target de-duplication (unique_count_hash, core/unique.cpp:243-334: its
+// CityHash table is only the device that finds the distinct k-mers) and the grouping by list in one go.
+constexpr uint64_t SPARSE_INVALID = 1ull << 45;
+__global__ void sparse_keys_kernel(DevSeqs db, int t0, int nt, int k, int mask_lower, const int64_t * __restrict__ cum,
+                                   uint64_t * __restrict__ keys)
+{
+  int const lt = blockIdx.x;
+  if (lt >= nt) { return; }
+  int64_t const t = static_cast<int64_t>(t0) + lt;
+  const uint8_t * __restrict__ s = db.sym + db.off[t];
+  int const len = db.len[t];
+  uint64_t * __restrict__ out = keys + cum[lt];
+  uint64_t const low = (static_cast<uint64_t>(lt & 1) << 14) | static_cast<uint64_t>(lt >> 1);
+  for (int p = threadIdx.x; p < len; p += blockDim.x) {
+    uint64_t key = SPARSE_INVALID;
+    uint32_t km;
+    if (p >= k - 1 && kmer_at(s, p, k, mask_lower, km)) { key = (static_cast<uint64_t>(km) << 15) | low; }
+    out[p] = key;
+  }
+}
+struct SparseRunOf {   // key -> sub-list id (k-mer << 1 | parity); the invalid key maps to 0x80000000
+  __host__ __device__ uint32_t operator()(uint64_t key) const { return static_cast<uint32_t>(key >> 14); }
+};
+struct PadTo8 {
+  __host__ __device__ uint32_t operator()(uint32_t n) const { return (n + 7u) & ~7u; }
+};
+// sub-list r: its distinct keys ukeys[src[r] .. src[r] + cnt[r]) become counter offsets at post[dst[r] ...]
+__global__ void sparse_scatter_kernel(const uint64_t * __restrict__ ukeys, const uint32_t * __restrict__ rkeys,
+                                      const uint32_t * __restrict__ cnt, const uint32_t * __restrict__ src,
+                                      const uint32_t * __restrict__ dst, uint32_t nr, uint16_t * __restrict__ post,
+                                      uint32_t * __restrict__ totals)
+{
+  uint32_t const r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nr) { return; }
+  uint32_t const n = cnt[r], a = src[r], b = dst[r];
+  for (uint32_t i = 0; i < n; i++) { post[b + i] = static_cast<uint16_t>((ukeys[a + i] & 0x3fffu) << 2); }
+  if (totals != nullptr) { atomicAdd(&totals[rkeys[r] >> 1], n); }
 }
 
 // Order inside a list does not matter to the counts, only to the speed of the shared-memory atomics that apply it:
@@ -272,14 +327,34 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
       //     distinct k-mers in a list there, and feed them through shared memory KMER_CAP at a time
       uint32_t * const bm = scratch + static_cast<size_t>(blockIdx.x) * scratch_stride;
       gk = bm + bitmap_words;
-      for (int i = threadIdx.x; i < bitmap_words; i += blockDim.x) { bm[i] = 0; }
-      __syncthreads();
-      for (int p = threadIdx.x; p < nwin; p += blockDim.x) {
-        uint32_t v;
-        if (kmer_at(s, p + k - 1, k, mask_lower, v)) {
-          uint32_t const bit = 1u << (v & 31);
-          uint32_t const old = atomicOr(&bm[v >> 5], bit);
-          if ((old & bit) == 0) { gk[atomicAdd(&s_nk, 1)] = v; }
+      if (k <= 10) {
+        for (int i = threadIdx.x; i < bitmap_words; i += blockDim.x) { bm[i] = 0; }
+        __syncthreads();
+        for (int p = threadIdx.x; p < nwin; p += blockDim.x) {
+          uint32_t v;
+          if (kmer_at(s, p + k - 1, k, mask_lower, v)) {
+            uint32_t const bit = 1u << (v & 31);
+            uint32_t const old = atomicOr(&bm[v >> 5], bit);
+            if ((old & bit) == 0) { gk[atomicAdd(&s_nk, 1)] = v; }
+          }
+        }
+      } else {
+        // wordlength 11..15: a 4^k-bit map per CTA is out of reach; an open-addressing table of bitmap_words (a power
+        // of two >= twice the windows) slots does what unique_count_hash's table does (core/unique.cpp:243-334)
+        uint32_t const hmask = static_cast<uint32_t>(bitmap_words) - 1u;
+        for (int i = threadIdx.x; i < bitmap_words; i += blockDim.x) { bm[i] = 0xffffffffu; }
+        __syncthreads();
+        for (int p = threadIdx.x; p < nwin; p += blockDim.x) {
+          uint32_t v;
+          if (kmer_at(s, p + k - 1, k, mask_lower, v)) {
+            uint32_t slot = (v * 2654435761u) >> 7 & hmask;
+            for (;;) {
+              uint32_t const old = atomicCAS(&bm[slot], 0xffffffffu, v);
+              if (old == 0xffffffffu) { gk[atomicAdd(&s_nk, 1)] = v; break; }
+              if (old == v) { break; }
+              slot = (slot + 1u) & hmask;
+            }
+          }
         }
       }
       __threadfence_block();
@@ -337,11 +412,25 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
         uint32_t b = 0, n = 0;
         if (km != 0xffffffffu) {
           if (INCR) { b = S.start[km]; n = S.end[km] - b; }
-          else {
+          else if (S.nr == 0u) {
             // even sub-list [b, mid), odd sub-list [mid, end): lengths in vectors of 8, both in one word
             b = S.start[2 * km];
             uint32_t const mid = S.start[2 * km + 1], e = S.start[2 * km + 2];
             n = ((mid - b) >> 3) | (((e - mid) >> 3) << 16);
+          } else {
+            // sparse shard: lower bound of the even sub-list's key among the sub-lists that exist; the odd one, if
+            // present, is its neighbour, so the pair is one contiguous run of postings either way
+            uint32_t const want = km << 1;
+            uint32_t lo = 0, hi = S.nr;
+            while (lo < hi) {
+              uint32_t const mid = (lo + hi) >> 1;
+              if (__ldg(S.rkeys + mid) < want) { lo = mid + 1; } else { hi = mid; }
+            }
+            b = S.start[lo];
+            uint32_t na = 0, nb = 0, i = lo;
+            if (i < S.nr && __ldg(S.rkeys + i) == want) { na = (S.start[i + 1] - S.start[i]) >> 3; i++; }
+            if (i < S.nr && __ldg(S.rkeys + i) == (want | 1u)) { nb = (S.start[i + 1] - S.start[i]) >> 3; }
+            n = na | (nb << 16);
           }
         }
         lbeg[i] = b; llen[i] = n;
@@ -625,97 +714,240 @@ struct vsg_index {
   int mask_lower = 0;
   int64_t ntargets = 0;
   const vsg_seqset * db = nullptr;
-  std::vector<DevBuf> b_start, b_post;
+  std::vector<DevBuf> b_start, b_post, b_rkeys;
   std::vector<ShardDev> h_shards;
   DevBuf b_shards;
   int64_t total_postings = 0;
 };
 
-extern "C" int vsg_index_create(vsg_ctx * c, const vsg_seqset * db, int wordlength, int mask_lower,
-                                vsg_index ** out)
+extern "C" void vsg_index_destroy(vsg_index * ix);
+namespace vsg {
+
+static void shard_bank_order(vsg_ctx * c, const uint32_t * start, uint16_t * post, size_t nlists)
 {
-  if (c == nullptr || db == nullptr || out == nullptr) { Error::set("vsg_index_create: null argument"); return VSG_EINVAL; }
-  *out = nullptr;
-  if (wordlength < 3 || wordlength > 10) {
-    Error::set("vsg_index_create: the device index supports --wordlength 3..10 (reference: 3..15)");
-    return VSG_EINVAL;
-  }
-  if (db->d.n > (1 << 24)) { Error::set("vsg_index_create: more than 2^24 targets"); return VSG_EINVAL; }
-  VSG_CUDA_OK(cudaSetDevice(c->device));
-  vsg_index * ix = new (std::nothrow) vsg_index();
-  if (ix == nullptr) { Error::set("out of host memory"); return VSG_ENOMEM; }
-  ix->device = c->device; ix->k = wordlength; ix->mask_lower = mask_lower; ix->ntargets = db->d.n; ix->db = db;
-  int const k = wordlength;
+  static bool const bank_order = [] { const char * e = std::getenv("VSG_BANK_ORDER"); return e == nullptr || e[0] != '0'; }();
+  if (!bank_order || nlists == 0) { return; }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  list_bank_order_kernel<<<static_cast<int>(std::min<size_t>(nlists, static_cast<size_t>(sms) * 32)), 128, 0, c->stream>>>(start, post, static_cast<int>(nlists));
+  count_launch();
+}
+
+// dense shard (k <= 10): start[2 * 4^k + 1], two sub-lists per k-mer
+static int build_dense_shard(vsg_ctx * c, vsg_index * ix, int sh, int t0, int nt, DevBuf & cnt, DevBuf & tmp, uint32_t * d_totals)
+{
+  const vsg_seqset * db = ix->db;
+  int const k = ix->k;
   size_t const hashsize = static_cast<size_t>(1) << (2 * k);
   size_t const bitmap_bytes = std::max<size_t>(hashsize / 8, 4);
-  if (bitmap_bytes > 48 * 1024) {
-    VSG_CUDA_OK(cudaFuncSetAttribute(index_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bitmap_bytes)));
-    VSG_CUDA_OK(cudaFuncSetAttribute(index_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bitmap_bytes)));
-  }
-  int const nshards = static_cast<int>((db->d.n + SHARD_STATIC - 1) / SHARD_STATIC);
   size_t const nlists = 2 * hashsize;   // even and odd targets of every k-mer
-  ix->b_start.resize(static_cast<size_t>(nshards));
-  ix->b_post.resize(static_cast<size_t>(nshards));
-  DevBuf cnt, tmp;
   int rc;
-  if ((rc = cnt.reserve(sizeof(uint32_t) * (nlists + 1))) != VSG_OK) { vsg_index_destroy(ix); return rc; }
-  for (int sh = 0; sh < nshards; sh++) {
-    int const t0 = sh * SHARD_STATIC;
-    int const nt = static_cast<int>(std::min<int64_t>(SHARD_STATIC, db->d.n - t0));
-    DevBuf & bs = ix->b_start[static_cast<size_t>(sh)];
-    if ((rc = bs.reserve(sizeof(uint32_t) * (nlists + 1))) != VSG_OK) { vsg_index_destroy(ix); return rc; }
-    VSG_CUDA_OK(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * (nlists + 1), c->stream));
-    index_build_kernel<false><<<nt, 128, bitmap_bytes, c->stream>>>(db->d, t0, nt, k, mask_lower, 1,
-                                                                    static_cast<uint32_t *>(cnt.p), nullptr, nullptr);
+  DevBuf & bs = ix->b_start[static_cast<size_t>(sh)];
+  if ((rc = bs.reserve(sizeof(uint32_t) * (nlists + 1))) != VSG_OK) { return rc; }
+  VSG_CUDA_OK(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * (nlists + 1), c->stream));
+  index_build_kernel<false><<<nt, 128, bitmap_bytes, c->stream>>>(db->d, t0, nt, k, ix->mask_lower, 1,
+                                                                  static_cast<uint32_t *>(cnt.p), nullptr, nullptr);
+  count_launch();
+  if (d_totals != nullptr) {
+    add_totals_kernel<<<static_cast<unsigned>((hashsize + 255) / 256), 256, 0, c->stream>>>(static_cast<const uint32_t *>(cnt.p), d_totals, hashsize);
     count_launch();
-    pad_counts_kernel<<<static_cast<unsigned>((nlists + 255) / 256), 256, 0, c->stream>>>(static_cast<uint32_t *>(cnt.p), static_cast<int>(nlists));
+  }
+  pad_counts_kernel<<<static_cast<unsigned>((nlists + 255) / 256), 256, 0, c->stream>>>(static_cast<uint32_t *>(cnt.p), static_cast<int>(nlists));
+  count_launch();
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, static_cast<uint32_t *>(cnt.p), static_cast<uint32_t *>(bs.p),
+                                static_cast<int>(nlists + 1), c->stream);
+  if ((rc = tmp.reserve(tb + 16)) != VSG_OK) { return rc; }
+  cub::DeviceScan::ExclusiveSum(tmp.p, tb, static_cast<uint32_t *>(cnt.p), static_cast<uint32_t *>(bs.p),
+                                static_cast<int>(nlists + 1), c->stream);
+  count_launch();
+  uint32_t total = 0;
+  VSG_CUDA_OK(cudaMemcpyAsync(&total, static_cast<uint32_t *>(bs.p) + nlists, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+  DevBuf & bp = ix->b_post[static_cast<size_t>(sh)];
+  if ((rc = bp.reserve(sizeof(uint16_t) * (static_cast<size_t>(total) + 64))) != VSG_OK) { return rc; }
+  VSG_CUDA_OK(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * (nlists + 1), c->stream));
+  if (total > 0) {
+    fill_u16_kernel<<<static_cast<unsigned>((static_cast<size_t>(total) + 255) / 256), 256, 0, c->stream>>>(
+        static_cast<uint16_t *>(bp.p), static_cast<size_t>(total), POST_PAD);
     count_launch();
-    size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, static_cast<uint32_t *>(cnt.p), static_cast<uint32_t *>(bs.p),
-                                  static_cast<int>(nlists + 1), c->stream);
-    if ((rc = tmp.reserve(tb + 16)) != VSG_OK) { vsg_index_destroy(ix); return rc; }
-    cub::DeviceScan::ExclusiveSum(tmp.p, tb, static_cast<uint32_t *>(cnt.p), static_cast<uint32_t *>(bs.p),
-                                  static_cast<int>(nlists + 1), c->stream);
+  }
+  index_build_kernel<true><<<nt, 128, bitmap_bytes, c->stream>>>(db->d, t0, nt, k, ix->mask_lower, 1,
+                                                                 static_cast<uint32_t *>(cnt.p),
+                                                                 static_cast<uint32_t *>(bs.p),
+                                                                 static_cast<uint16_t *>(bp.p));
+  count_launch();
+  if (total > 0) { shard_bank_order(c, static_cast<const uint32_t *>(bs.p), static_cast<uint16_t *>(bp.p), nlists); }
+  ShardDev sd{};
+  sd.start = static_cast<uint32_t *>(bs.p); sd.post = static_cast<uint16_t *>(bp.p); sd.t0 = t0; sd.nt = nt;
+  ix->h_shards.push_back(sd);
+  ix->total_postings += total;
+  return VSG_OK;
+}
+
+// sparse shard (k 11..15): sort the windows' keys, drop duplicates, run-length encode the sub-lists
+struct SparseScratch { DevBuf keys0, keys1, runs, cum, num, tmp; void release() { keys0.release(); keys1.release(); runs.release(); cum.release(); num.release(); tmp.release(); } };
+static int build_sparse_shard(vsg_ctx * c, vsg_index * ix, int sh, int t0, int nt, SparseScratch & w, uint32_t * d_totals)
+{
+  const vsg_seqset * db = ix->db;
+  int rc;
+  // window slots of the shard's targets back to back, whatever the layout of the sequence set
+  std::vector<int64_t> cum(static_cast<size_t>(nt) + 1, 0);
+  for (int i = 0; i < nt; i++) { cum[static_cast<size_t>(i) + 1] = cum[static_cast<size_t>(i)] + db->h_len[static_cast<size_t>(t0) + static_cast<size_t>(i)]; }
+  int64_t const W = cum[static_cast<size_t>(nt)];
+  if (W >= (static_cast<int64_t>(1) << 31) - 64) { Error::set("vsg_index_create: a shard of 32766 targets holds 2^31 nucleotides or more (wordlength > 10)"); return VSG_EINVAL; }
+  DevBuf & bs = ix->b_start[static_cast<size_t>(sh)];
+  DevBuf & bp = ix->b_post[static_cast<size_t>(sh)];
+  DevBuf & bk = ix->b_rkeys[static_cast<size_t>(sh)];
+  int const n = static_cast<int>(W);
+  uint32_t nr = 0, total = 0;
+  if (n > 0) {
+    if ((rc = w.keys0.reserve(sizeof(uint64_t) * (static_cast<size_t>(n) + 8))) != VSG_OK ||
+        (rc = w.keys1.reserve(sizeof(uint64_t) * (static_cast<size_t>(n) + 8))) != VSG_OK ||
+        (rc = w.cum.reserve(sizeof(int64_t) * (static_cast<size_t>(nt) + 1))) != VSG_OK ||
+        (rc = w.num.reserve(64)) != VSG_OK) { return rc; }
+    uint64_t * const k0 = static_cast<uint64_t *>(w.keys0.p);
+    uint64_t * const k1 = static_cast<uint64_t *>(w.keys1.p);
+    uint32_t * const d_num = static_cast<uint32_t *>(w.num.p);
+    VSG_CUDA_OK(cudaMemcpyAsync(w.cum.p, cum.data(), sizeof(int64_t) * (static_cast<size_t>(nt) + 1), cudaMemcpyHostToDevice, c->stream));
+    sparse_keys_kernel<<<nt, 128, 0, c->stream>>>(db->d, t0, nt, ix->k, ix->mask_lower, static_cast<const int64_t *>(w.cum.p), k0);
     count_launch();
-    uint32_t total = 0;
-    VSG_CUDA_OK(cudaMemcpyAsync(&total, static_cast<uint32_t *>(bs.p) + nlists, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    VSG_CUDA_OK(cudaStreamSynchronize(c->stream));   // `cum` (pageable) has been consumed
+    size_t tb = 0, tb2 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tb, k0, k1, n, 0, 46, c->stream);
+    cub::DeviceSelect::Unique(nullptr, tb2, k1, k0, d_num, n, c->stream);
+    if ((rc = w.tmp.reserve(std::max(tb, tb2) + 64)) != VSG_OK) { return rc; }
+    cub::DeviceRadixSort::SortKeys(w.tmp.p, tb, k0, k1, n, 0, 46, c->stream);
+    count_launch();
+    cub::DeviceSelect::Unique(w.tmp.p, tb2, k1, k0, d_num, n, c->stream);
+    count_launch();
+    uint32_t nu = 0;
+    VSG_CUDA_OK(cudaMemcpyAsync(&nu, d_num, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
-    DevBuf & bp = ix->b_post[static_cast<size_t>(sh)];
-    if ((rc = bp.reserve(sizeof(uint16_t) * (static_cast<size_t>(total) + 64))) != VSG_OK) { vsg_index_destroy(ix); return rc; }
-    VSG_CUDA_OK(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * (nlists + 1), c->stream));
-    if (total > 0) {
+    // k0[0 .. nu): the distinct keys in order, closed by the invalid key if any window was unusable.
+    // Sub-lists = runs of key >> 14; the invalid key's run has id 0x80000000 and comes last.
+    if ((rc = w.runs.reserve(sizeof(uint32_t) * 2 * (static_cast<size_t>(nu) + 2))) != VSG_OK ||
+        (rc = bk.reserve(sizeof(uint32_t) * (static_cast<size_t>(nu) + 2))) != VSG_OK) { return rc; }
+    uint32_t * const rcnt = static_cast<uint32_t *>(w.runs.p);
+    uint32_t * const rsrc = rcnt + nu + 2;
+    uint32_t * const rkeys = static_cast<uint32_t *>(bk.p);
+    VSG_CUDA_OK(cudaMemsetAsync(rcnt, 0, sizeof(uint32_t) * 2 * (static_cast<size_t>(nu) + 2), c->stream));
+    uint32_t nruns = 0;
+    if (nu > 0) {
+      auto runs_in = thrust::make_transform_iterator(static_cast<const uint64_t *>(k0), SparseRunOf());
+      size_t tb3 = 0;
+      cub::DeviceRunLengthEncode::Encode(nullptr, tb3, runs_in, rkeys, rcnt, d_num, static_cast<int>(nu), c->stream);
+      if ((rc = w.tmp.reserve(tb3 + 64)) != VSG_OK) { return rc; }
+      cub::DeviceRunLengthEncode::Encode(w.tmp.p, tb3, runs_in, rkeys, rcnt, d_num, static_cast<int>(nu), c->stream);
+      count_launch();
+      VSG_CUDA_OK(cudaMemcpyAsync(&nruns, d_num, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+      VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+      if (nruns > 0) {
+        uint32_t lastkey = 0;
+        VSG_CUDA_OK(cudaMemcpyAsync(&lastkey, rkeys + (nruns - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+        if (lastkey >= 0x80000000u) { nruns--; }
+      }
+    }
+    nr = nruns;
+    if (nr > 0) {
+      if ((rc = bs.reserve(sizeof(uint32_t) * (static_cast<size_t>(nr) + 2))) != VSG_OK) { return rc; }
+      // source offsets (plain counts) and destination offsets (counts padded to vectors of 8) of every sub-list
+      size_t tb4 = 0, tb5 = 0;
+      auto padded = thrust::make_transform_iterator(static_cast<const uint32_t *>(rcnt), PadTo8());
+      cub::DeviceScan::ExclusiveSum(nullptr, tb4, rcnt, rsrc, static_cast<int>(nr + 1), c->stream);
+      cub::DeviceScan::ExclusiveSum(nullptr, tb5, padded, static_cast<uint32_t *>(bs.p), static_cast<int>(nr + 1), c->stream);
+      if ((rc = w.tmp.reserve(std::max(tb4, tb5) + 64)) != VSG_OK) { return rc; }
+      cub::DeviceScan::ExclusiveSum(w.tmp.p, tb4, rcnt, rsrc, static_cast<int>(nr + 1), c->stream);
+      count_launch();
+      cub::DeviceScan::ExclusiveSum(w.tmp.p, tb5, padded, static_cast<uint32_t *>(bs.p), static_cast<int>(nr + 1), c->stream);
+      count_launch();
+      VSG_CUDA_OK(cudaMemcpyAsync(&total, static_cast<uint32_t *>(bs.p) + nr, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+      VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
+      if ((rc = bp.reserve(sizeof(uint16_t) * (static_cast<size_t>(total) + 64))) != VSG_OK) { return rc; }
       fill_u16_kernel<<<static_cast<unsigned>((static_cast<size_t>(total) + 255) / 256), 256, 0, c->stream>>>(
           static_cast<uint16_t *>(bp.p), static_cast<size_t>(total), POST_PAD);
       count_launch();
-    }
-    index_build_kernel<true><<<nt, 128, bitmap_bytes, c->stream>>>(db->d, t0, nt, k, mask_lower, 1,
-                                                                   static_cast<uint32_t *>(cnt.p),
-                                                                   static_cast<uint32_t *>(bs.p),
-                                                                   static_cast<uint16_t *>(bp.p));
-    count_launch();
-    static bool const bank_order = [] { const char * e = std::getenv("VSG_BANK_ORDER"); return e == nullptr || e[0] != '0'; }();
-    if (total > 0 && bank_order) {
-      int sms = 148;
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-      list_bank_order_kernel<<<std::min<int>(static_cast<int>(nlists), sms * 32), 128, 0, c->stream>>>(
-          static_cast<const uint32_t *>(bs.p), static_cast<uint16_t *>(bp.p), static_cast<int>(nlists));
+      sparse_scatter_kernel<<<(nr + 127) / 128, 128, 0, c->stream>>>(k0, rkeys, rcnt, rsrc, static_cast<const uint32_t *>(bs.p), nr,
+                                                                    static_cast<uint16_t *>(bp.p), d_totals);
       count_launch();
+      shard_bank_order(c, static_cast<const uint32_t *>(bs.p), static_cast<uint16_t *>(bp.p), nr);
+      VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
     }
-    ShardDev sd;
-    sd.start = static_cast<uint32_t *>(bs.p); sd.post = static_cast<uint16_t *>(bp.p); sd.t0 = t0; sd.nt = nt;
-    sd.end = nullptr; sd.post32 = nullptr;
-    ix->h_shards.push_back(sd);
-    ix->total_postings += total;
   }
-  if ((rc = ix->b_shards.reserve(sizeof(ShardDev) * (ix->h_shards.size() + 1))) != VSG_OK) { vsg_index_destroy(ix); return rc; }
-  if (!ix->h_shards.empty()) {
-    VSG_CUDA_OK(cudaMemcpyAsync(ix->b_shards.p, ix->h_shards.data(), sizeof(ShardDev) * ix->h_shards.size(), cudaMemcpyHostToDevice, c->stream));
+  if (nr == 0) {
+    // no usable window in the whole shard: one empty sub-list under a key no k-mer has
+    if ((rc = bs.reserve(16)) != VSG_OK || (rc = bp.reserve(128)) != VSG_OK || (rc = bk.reserve(16)) != VSG_OK) { return rc; }
+    VSG_CUDA_OK(cudaMemsetAsync(bs.p, 0, 16, c->stream));
+    VSG_CUDA_OK(cudaMemsetAsync(bk.p, 0xff, 16, c->stream));
+    nr = 1;
   }
-  VSG_CUDA_OK(cudaStreamSynchronize(c->stream));
-  VSG_CUDA_OK(cudaGetLastError());
-  cnt.release(); tmp.release();
+  ShardDev sd{};
+  sd.t0 = t0; sd.nt = nt;
+  sd.start = static_cast<uint32_t *>(bs.p); sd.post = static_cast<uint16_t *>(bp.p);
+  sd.rkeys = static_cast<uint32_t *>(bk.p); sd.nr = nr;
+  ix->h_shards.push_back(sd);
+  ix->total_postings += total;
+  return VSG_OK;
+}
+
+// d_totals (optional): 4^k words on the device, zeroed by the caller; receives the number of targets holding each k-mer
+int index_create_counts(vsg_ctx * c, const vsg_seqset * db, int wordlength, int mask_lower, uint32_t * d_totals, vsg_index ** out)
+{
+  if (c == nullptr || db == nullptr || out == nullptr) { Error::set("vsg_index_create: null argument"); return VSG_EINVAL; }
+  *out = nullptr;
+  if (wordlength < 3 || wordlength > 15) {
+    Error::set("vsg_index_create: --wordlength must be in 3..15");
+    return VSG_EINVAL;
+  }
+  if (db->device != c->device) { Error::set("vsg_index_create: the sequence set lives on another device than the context"); return VSG_EINVAL; }
+  if (db->d.n > (1 << 24)) { Error::set("vsg_index_create: more than 2^24 targets"); return VSG_EINVAL; }
+  VSG_CUDA_OK(cudaSetDevice(c->device));
+  int const k = wordlength;
+  bool const sparse = k > 10;
+  size_t const hashsize = static_cast<size_t>(1) << (2 * k);
+  if (!sparse) {
+    size_t const bitmap_bytes = std::max<size_t>(hashsize / 8, 4);
+    if (bitmap_bytes > 48 * 1024) {
+      VSG_CUDA_OK(cudaFuncSetAttribute(index_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bitmap_bytes)));
+      VSG_CUDA_OK(cudaFuncSetAttribute(index_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bitmap_bytes)));
+    }
+  }
+  vsg_index * ix = new (std::nothrow) vsg_index();
+  if (ix == nullptr) { Error::set("out of host memory"); return VSG_ENOMEM; }
+  ix->device = c->device; ix->k = wordlength; ix->mask_lower = mask_lower; ix->ntargets = db->d.n; ix->db = db;
+  int const nshards = static_cast<int>((db->d.n + SHARD_STATIC - 1) / SHARD_STATIC);
+  ix->b_start.resize(static_cast<size_t>(nshards));
+  ix->b_post.resize(static_cast<size_t>(nshards));
+  ix->b_rkeys.resize(static_cast<size_t>(nshards));
+  DevBuf cnt, tmp;
+  SparseScratch w;
+  int rc = VSG_OK;
+  if (!sparse) { rc = cnt.reserve(sizeof(uint32_t) * (2 * hashsize + 1)); }
+  for (int sh = 0; sh < nshards && rc == VSG_OK; sh++) {
+    int const t0 = sh * SHARD_STATIC;
+    int const nt = static_cast<int>(std::min<int64_t>(SHARD_STATIC, db->d.n - t0));
+    rc = sparse ? build_sparse_shard(c, ix, sh, t0, nt, w, d_totals) : build_dense_shard(c, ix, sh, t0, nt, cnt, tmp, d_totals);
+  }
+  if (rc == VSG_OK) { rc = ix->b_shards.reserve(sizeof(ShardDev) * (ix->h_shards.size() + 1)); }
+  cudaError_t e = cudaSuccess;
+  if (rc == VSG_OK && !ix->h_shards.empty()) {
+    e = cudaMemcpyAsync(ix->b_shards.p, ix->h_shards.data(), sizeof(ShardDev) * ix->h_shards.size(), cudaMemcpyHostToDevice, c->stream);
+  }
+  if (rc == VSG_OK && e == cudaSuccess) { e = cudaStreamSynchronize(c->stream); }
+  if (rc == VSG_OK && e == cudaSuccess) { e = cudaGetLastError(); }
+  cnt.release(); tmp.release(); w.release();
+  if (rc == VSG_OK && e != cudaSuccess) { Error::set(std::string("vsg_index_create: ") + cudaGetErrorString(e)); rc = VSG_ECUDA; }
+  if (rc != VSG_OK) { vsg_index_destroy(ix); return rc; }
   *out = ix;
   return VSG_OK;
+}
+}  // namespace vsg
+
+extern "C" int vsg_index_create(vsg_ctx * c, const vsg_seqset * db, int wordlength, int mask_lower,
+                                vsg_index ** out)
+{
+  return vsg::index_create_counts(c, db, wordlength, mask_lower, nullptr, out);
 }
 
 extern "C" void vsg_index_destroy(vsg_index * ix)
@@ -724,6 +956,7 @@ extern "C" void vsg_index_destroy(vsg_index * ix)
   cudaSetDevice(ix->device);
   for (auto & b : ix->b_start) { b.release(); }
   for (auto & b : ix->b_post) { b.release(); }
+  for (auto & b : ix->b_rkeys) { b.release(); }
   ix->b_shards.release();
   delete ix;
 }
@@ -760,7 +993,8 @@ int rank_enqueue(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * queries, 
   for (int64_t q = q0; q < q0 + nq; q++) { maxlen = std::max(maxlen, queries->h_len[static_cast<size_t>(q)]); }
   uint32_t * d_scratch = nullptr;
   size_t stride = 0;
-  int const bitmap_words = std::max(1, (1 << (2 * ix->k)) >> 5);
+  int bitmap_words = std::max(1, (1 << (2 * std::min(ix->k, 10))) >> 5);
+  if (ix->k > 10) { bitmap_words = 4096; while (bitmap_words < 2 * maxlen) { bitmap_words <<= 1; } }   // hash slots (power of two)
   if (maxlen - ix->k + 1 > KMER_CAP) {
     stride = static_cast<size_t>(bitmap_words) + static_cast<size_t>(maxlen) + 8;
     if ((rc = c->rank_scratch.reserve(sizeof(uint32_t) * stride * static_cast<size_t>(grid))) != VSG_OK) { return rc; }
@@ -986,6 +1220,7 @@ int cindex_rank_enqueue(vsg_ctx * c, CIndex * ix, const vsg_seqset * queries, in
     sd.start = static_cast<const uint32_t *>(s == 0 ? ix->b_start.p : ix->b_begin[static_cast<size_t>(s) - 1].p);
     sd.end = static_cast<const uint32_t *>(s + 1 < nshards || ix->ncent % SHARD == 0 ? ix->b_begin[static_cast<size_t>(s)].p : ix->b_cursor.p);
     sd.post = nullptr; sd.post32 = static_cast<const uint32_t *>(ix->b_post.p);
+    sd.rkeys = nullptr; sd.nr = 0; sd.reserved = 0;
     sd.t0 = s * SHARD;
     sd.nt = static_cast<int32_t>(std::min<int64_t>(SHARD, ix->ncent - static_cast<int64_t>(s) * SHARD));
   }

@@ -94,6 +94,7 @@ def load():
     lib.vsg_group_ctx.restype = C.c_void_p
     lib.vsg_group_db.restype = C.c_void_p
     lib.vsg_group_index.restype = C.c_void_p
+    lib.vsg_udb_header.restype = C.c_char_p
     _lib = lib
     return lib
 
@@ -268,6 +269,13 @@ class Context:
                                        C.byref(h)), "vsg_index_create")
         return IndexHandle(h)
 
+    def udb_load(self, udb: "Udb"):
+        """vsg_udb_load: (SeqSetHandle, IndexHandle, mask_lower) of a parsed UDB file"""
+        sh = C.c_void_p(); ih = C.c_void_p(); ml = C.c_int(-1)
+        _check(load().vsg_udb_load(self.h, udb.h, C.byref(sh), C.byref(ih), C.byref(ml)), "vsg_udb_load")
+        _, _, lens = udb.sequences()
+        return SeqSetHandle(self, sh, udb.n, lens), IndexHandle(ih), int(ml.value)
+
     def rank(self, ix: IndexHandle, qs: SeqSetHandle, q0: int, nq: int, minwordmatches: int,
              tophits: int, mask_lower: int = 0):
         seqno = np.zeros((nq, tophits), dtype=np.uint32)
@@ -374,6 +382,21 @@ class Group:
                                     _ptr(offs, C.c_int64), _ptr(lens, C.c_int32), C.c_int64(self.n), C.c_int(wordlength),
                                     C.c_int(mask_lower), C.c_int(dust_db), C.byref(self.h)), "vsg_group_create")
 
+    @classmethod
+    def from_udb(cls, devices, udb: "Udb", pen=DEFAULT_PEN, n_mismatch=0):
+        """vsg_group_create_udb: the database of a parsed UDB file on every device"""
+        self = cls.__new__(cls)
+        sc = Scoring()
+        for i in range(14):
+            sc.v[i] = int(pen[i])
+        sc.n_mismatch = int(n_mismatch)
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        self.h = C.c_void_p()
+        self.n = udb.n
+        _check(load().vsg_group_create_udb(_ptr(dev, C.c_int), C.c_int(dev.shape[0]), C.byref(sc), udb.h, C.byref(self.h)),
+               "vsg_group_create_udb")
+        return self
+
     def close(self):
         if self.h:
             load().vsg_group_destroy(self.h)
@@ -418,6 +441,56 @@ class Group:
                                          C.c_int(batch_queries), C.c_int64(maxhits), C.c_int(output_no_hits), blast6out.encode(),
                                          C.byref(st)), "vsg_usearch_stream")
         return {k: getattr(st, k) for k, _ in StreamStats._fields_}
+
+
+class UdbInfo(C.Structure):
+    _fields_ = [("sequences", C.c_int64), ("nucleotides", C.c_int64), ("header_chars", C.c_int64), ("index_entries", C.c_int64),
+                ("longest_header", C.c_int64), ("wordlength", C.c_int32), ("dbaccel", C.c_int32), ("shortest", C.c_int32),
+                ("longest", C.c_int32)]
+
+
+def udb_detect(path: str) -> bool:
+    rc = load().vsg_udb_detect(path.encode())
+    if rc < 0:
+        _check(rc, "vsg_udb_detect")
+    return rc == 1
+
+
+class Udb:
+    """A parsed UDB file (host side; no GPU needed): vsg_udb_open and its accessors."""
+
+    def __init__(self, path: str):
+        self.h = C.c_void_p()
+        _check(load().vsg_udb_open(path.encode(), C.byref(self.h)), "vsg_udb_open")
+        self.info = UdbInfo()
+        _check(load().vsg_udb_info_get(self.h, C.byref(self.info)), "vsg_udb_info_get")
+        self.n = int(self.info.sequences)
+
+    def close(self):
+        if self.h:
+            load().vsg_udb_close(self.h)
+            self.h = C.c_void_p()
+
+    def sequences(self):
+        """(cat bytes, offsets, lengths) as numpy copies"""
+        cat = C.c_char_p(); off = C.POINTER(C.c_int64)(); ln = C.POINTER(C.c_int32)()
+        cat_p = C.c_void_p()
+        _check(load().vsg_udb_sequences(self.h, C.byref(cat_p), C.byref(off), C.byref(ln)), "vsg_udb_sequences")
+        total = int(self.info.nucleotides)
+        catb = np.frombuffer(C.string_at(cat_p.value, total), dtype=np.uint8).copy()
+        return catb, np.ctypeslib.as_array(off, shape=(self.n,)).copy(), np.ctypeslib.as_array(ln, shape=(self.n,)).copy()
+
+    def header(self, i: int) -> str:
+        return load().vsg_udb_header(self.h, C.c_int64(i)).decode()
+
+    def words(self):
+        """the stored index: (kmercount[4^k], kmerindex[index_entries]) as numpy copies"""
+        kc = C.POINTER(C.c_uint32)(); ki = C.POINTER(C.c_uint32)()
+        _check(load().vsg_udb_words(self.h, C.byref(kc), C.byref(ki)), "vsg_udb_words")
+        nk = 1 << (2 * int(self.info.wordlength))
+        ne = int(self.info.index_entries)
+        return (np.ctypeslib.as_array(kc, shape=(nk,)).copy(),
+                np.ctypeslib.as_array(ki, shape=(ne,)).copy() if ne > 0 else np.zeros(0, dtype=np.uint32))
 
 
 class StreamStats(C.Structure):
