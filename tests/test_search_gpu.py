@@ -226,6 +226,36 @@ def test_search_vs_compiled_reference(ctx):
 
 
 @pytest.mark.skipif(checkers.ref() is None, reason="oracle/_ref/libvsref.so not present")
+@pytest.mark.parametrize("maxaccepts,ident", [(1, 0.9), (1, 0.97), (3, 0.9)])
+def test_traceback_on_demand_does_not_change_the_hit_tables(ctx, maxaccepts, ident):
+    """the followers of a group are walked back only when the leader is not accepted (align_ckpt.cuh, TbGate): same rows
+    with the shortcut off, on, and with a device verdict that is always "accepted" (every needed follower re-aligned by
+    the replay).  id 0.97 puts many leaders below the threshold (5 % mutated queries)."""
+    dbs, qss, src = synth.config2_search(n_db=600, db_len=1500, n_q=400, q_len=250, div=0.05, seed=91)
+    r = checkers.RefDb(dbs, id=ident, maxaccepts=maxaccepts, maxrejects=16)
+    want = r.search(qss, max_results=r.tophits)
+    th = r.tophits
+    r.close()
+    db = ctx.seqset(dbs); qs = ctx.seqset(qss)
+    ix = ctx.index(db, 8, 0)
+    os.environ["VSG_CKPT_MIN_PAIRS"] = "0"     # the checkpoint kernels at this call size too
+    try:
+        for env in ({"VSG_TB_GATE": "0"}, {}, {"VSG_TB_GATE_FORCE": "1"}):
+            os.environ.update(env)
+            try:
+                with no_tail():
+                    res, counts, work = ctx.search(ix, db, qs, 0, len(qss), gpu_opts(ident, maxaccepts, 16), th)
+            finally:
+                for k in env:
+                    del os.environ[k]
+            for i in range(len(qss)):
+                assert rows_of(res, counts, i, th) == [list(t) for t in want[i]], (env, i)
+    finally:
+        del os.environ["VSG_CKPT_MIN_PAIRS"]
+    ix.close(); db.close(); qs.close()
+
+
+@pytest.mark.skipif(checkers.ref() is None, reason="oracle/_ref/libvsref.so not present")
 def test_deferred_pairs_go_through_the_fallback_callback(ctx):
     """pairs the 16-bit aligner cannot take (q*d > 25e6) are resolved by the host application's
     linear-memory aligner through vsg_ctx_set_fallback — here the reference's own LinearMemoryAligner —

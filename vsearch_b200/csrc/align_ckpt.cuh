@@ -407,14 +407,54 @@ __device__ __forceinline__ void traceback_ckpt_one(const ScoreParams & sp, const
 // alone is up to D/32 tiles), so a thread does not own one pair: the grid is sized to fill the device once, every
 // thread starts with pair = its global index and, whenever its alignment is finished, takes the next unclaimed pair
 // from a ticket counter while the other lanes of its warp carry on with theirs.  *ticket must be 0 at launch.
+// TRACEBACK ON DEMAND (the batched search driver).  align_delayed hands search16 a group of up to eight candidates of
+// a query and then examines them in order until the accept / reject limits are reached (searchcore.cpp:780-880): when
+// the first one is accepted and that accept is the last one wanted, the other seven alignments are never looked at.
+// Their DP is computed here like every other pair's (it is the work the metric counts), but their walk back through
+// the matrix is not: the group's LEADER is walked first (phase 1; its thread also stores the verdict of
+// search_acceptable_aligned's identity test next to its statistics), the FOLLOWERS afterwards (phase 2), and a follower
+// whose leader was accepted leaves its statistics "not computed" (all bits set).  The verdict is taken with a small
+// margin, so a borderline leader just means walked followers; the host replay re-aligns a pair it needs and finds
+// not computed (search.cu), which keeps the results independent of this shortcut.
+constexpr int32_t TB_VERDICT_ACCEPTED = 0x5ca1ab1e;
+struct TbGate {
+  const int * ids;            // pair ids (2 * task + half) this launch handles, nids of them; nullptr = all pairs of the tasks
+  int nids;
+  const int32_t * leader_of;  // per pair slot: slot of its leader, -1 = none (a leader, or not gated); nullptr = no gating
+  int phase;                  // 1: leaders (store the verdict), 2: followers (skip when the leader was accepted)
+  int iddef;                  // --iddef
+  double threshold;           // 100 * --id + margin
+};
+
+// the identity of align_trim + search_acceptable_aligned's test for a hit with the default optional filters
+// (hit_logic.h finish_hit / acceptable_aligned, searchcore.cpp:409-463, 664-737)
+__device__ __forceinline__ bool tb_leader_accepted(const ckpt::TbOut & o, int Q, int D, int iddef, double threshold)
+{
+  int const nal = o.aligned, ma = o.matches, mi = o.mismatches, ga = o.gaps;
+  int const tql = o.trim_left > 0 ? o.trim_left : 0, ttl = o.trim_left < 0 ? -o.trim_left : 0;
+  int tqr = o.trim_right > 0 ? o.trim_right : 0, ttr = o.trim_right < 0 ? -o.trim_right : 0;
+  if (tql >= nal) { tqr = 0; }
+  if (ttl >= nal) { ttr = 0; }
+  int const internal = nal - (tql + ttl + tqr + ttr);
+  int const shortest = Q < D ? Q : D, longest = Q < D ? D : Q;
+  double id;
+  switch (iddef) {
+    case 0: id = shortest > 0 ? 100.0 * ma / shortest : 0.0; break;
+    case 2: id = internal > 0 ? 100.0 * ma / internal : 0.0; break;
+    case 3: { double const v = 100.0 * (1.0 - (1.0 * (mi + ga) / longest)); id = v > 0.0 ? v : 0.0; break; }
+    default: id = nal > 0 ? 100.0 * ma / nal : 0.0; break;   // 1 and 4
+  }
+  return ma > 0 && id >= threshold;
+}
+
 template <int RT, bool GENERAL>
 __device__ __forceinline__ void traceback_ckpt_tasks_body(const ScoreParams & sp, const DevSeqs & qs, const DevSeqs & ts,
                                                           const FastTask * __restrict__ tasks, int ntasks, int R,
                                                           const uint2 * __restrict__ rowck, const uint2 * __restrict__ colck,
                                                           int32_t * __restrict__ stats, int * __restrict__ ticket, int ticket_base,
-                                                          unsigned char * smem)
+                                                          const TbGate & gate, unsigned char * smem)
 {
-  int const total = 2 * ntasks;
+  int const total = gate.ids != nullptr ? gate.nids : 2 * ntasks;
   int const nthreads = gridDim.x * blockDim.x;
   SmemRows rows{nullptr, reinterpret_cast<uint4 *>(smem) + threadIdx.x};
   SmemBits<RT / 8> bits{reinterpret_cast<uint32_t *>(smem + static_cast<size_t>(TB_CK_ROWVECS) * TB_CK_THREADS * 16) + threadIdx.x};
@@ -422,15 +462,20 @@ __device__ __forceinline__ void traceback_ckpt_tasks_body(const ScoreParams & sp
   ckpt::Walk<RT, GENERAL> w;
   int next = blockIdx.x * blockDim.x + threadIdx.x;
   int out = -1;
+  int myQ = 0, myD = 0;
   bool active = false;
   for (;;) {
     while (!active && next < total) {
-      int const id = next;
+      int const id = gate.ids != nullptr ? gate.ids[next] : next;
       FastTask const tk = tasks[id >> 1];
       int const half = id & 1;
       out = half ? tk.out_hi : tk.out_lo;
       next = ticket_base >= total ? total : nthreads + atomicAdd(ticket, 1);
       if (out < 0) { continue; }
+      if (gate.leader_of != nullptr && gate.phase == 2) {
+        int const lead = gate.leader_of[out];
+        if (lead >= 0 && stats[static_cast<size_t>(lead) * VSG_STAT_WORDS + VSG_STAT_CIGARLEN] == TB_VERDICT_ACCEPTED) { continue; }
+      }
       uint32_t const q = tk.q, t = half ? tk.thi : tk.tlo;
       ckpt::PairView pv;
       pv.rowck = reinterpret_cast<const ckpt::U2 *>(rowck + tk.dir_off);
@@ -438,6 +483,7 @@ __device__ __forceinline__ void traceback_ckpt_tasks_body(const ScoreParams & sp
       pv.R = R; pv.half = half; pv.Q = qs.len[q]; pv.D = ts.len[t]; pv.general = GENERAL ? 1 : 0;
       pv.q = qs.sym + qs.off[q];
       pv.t = ts.sym + ts.off[t];
+      myQ = pv.Q; myD = pv.D;
       rows.rowck = rowck + tk.dir_off;
       w.start(pv);
       active = true;
@@ -451,7 +497,8 @@ __device__ __forceinline__ void traceback_ckpt_tasks_body(const ScoreParams & sp
         int32_t * const st = stats + static_cast<size_t>(out) * VSG_STAT_WORDS;
         st[VSG_STAT_ALIGNED] = o.aligned; st[VSG_STAT_MATCHES] = o.matches; st[VSG_STAT_MISMATCHES] = o.mismatches;
         st[VSG_STAT_GAPS] = o.gaps; st[VSG_STAT_TRIM_LEFT] = o.trim_left; st[VSG_STAT_TRIM_RIGHT] = o.trim_right;
-        st[VSG_STAT_CIGARLEN] = 0;
+        st[VSG_STAT_CIGARLEN] = (gate.leader_of != nullptr && gate.phase == 1 && tb_leader_accepted(o, myQ, myD, gate.iddef, gate.threshold))
+                                    ? TB_VERDICT_ACCEPTED : 0;
         active = false;
       }
     }
@@ -463,11 +510,11 @@ __global__ void __launch_bounds__(TB_CK_THREADS)
 traceback_ckpt_tasks_kernel(const __grid_constant__ ScoreParams sp, DevSeqs qs, DevSeqs ts,
                             const FastTask * __restrict__ tasks, int ntasks, int R, int general,
                             const uint2 * __restrict__ rowck, const uint2 * __restrict__ colck,
-                            int32_t * __restrict__ stats, int * __restrict__ ticket, int ticket_base)
+                            int32_t * __restrict__ stats, int * __restrict__ ticket, int ticket_base, TbGate gate)
 {
   extern __shared__ __align__(16) unsigned char tb_smem[];
-  if (general) { traceback_ckpt_tasks_body<RT, true>(sp, qs, ts, tasks, ntasks, R, rowck, colck, stats, ticket, ticket_base, tb_smem); }
-  else { traceback_ckpt_tasks_body<RT, false>(sp, qs, ts, tasks, ntasks, R, rowck, colck, stats, ticket, ticket_base, tb_smem); }
+  if (general) { traceback_ckpt_tasks_body<RT, true>(sp, qs, ts, tasks, ntasks, R, rowck, colck, stats, ticket, ticket_base, gate, tb_smem); }
+  else { traceback_ckpt_tasks_body<RT, false>(sp, qs, ts, tasks, ntasks, R, rowck, colck, stats, ticket, ticket_base, gate, tb_smem); }
 }
 
 // with CIGAR text, from pair descriptors (kind 2 = checkpoint layout; the others belong to traceback_kernel)

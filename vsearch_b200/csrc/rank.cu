@@ -31,6 +31,15 @@ namespace vsg {
 constexpr int SHARD_BITS = 15;
 constexpr int SHARD = 1 << SHARD_BITS;  // targets per shard
 constexpr int RANK_THREADS = 512;
+#ifndef VSG_RANK_U
+#define VSG_RANK_U 4      // posting vectors (of 8) a lane holds at a time
+#endif
+#ifndef VSG_RANK_ROLL
+#define VSG_RANK_ROLL 0   // 1: refill a slot as soon as it has been applied (measured: no gain, see DESIGN experiment log)
+#endif
+#ifndef VSG_RANK_ZFUSE
+#define VSG_RANK_ZFUSE 1  // clear the counters behind the last scan of a shard instead of in a pass of its own
+#endif
 constexpr int KMER_CAP = 2048;          // distinct-k-mer capacity per query (query length <= 2047 + k)
 constexpr int CAND_CAP = 2048;          // candidate keys held in shared memory
 constexpr int TOPHITS_MAX = 1024;
@@ -267,11 +276,11 @@ __device__ __forceinline__ uint64_t make_key(uint32_t count, uint32_t len, uint3
 }
 
 template <bool INCR>
-__global__ void __launch_bounds__(RANK_THREADS)
+__global__ void __launch_bounds__(RANK_THREADS, 2)
 rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restrict__ shards, int nshards,
             int k, int mask_lower, int minwordmatches, int tophits,
             uint32_t * __restrict__ out_seqno, uint32_t * __restrict__ out_count, int32_t * __restrict__ out_n,
-            int32_t * __restrict__ status, uint32_t * __restrict__ scratch, size_t scratch_stride, int bitmap_words)
+            int32_t * __restrict__ status, uint32_t * __restrict__ scratch, size_t scratch_stride, int bitmap_words, int flat)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   uint64_t * const cand = reinterpret_cast<uint64_t *>(smem);                     // CAND_CAP
@@ -279,12 +288,14 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
   uint32_t * const kmers = counters + COUNTER_WORDS + 3;                          // KMER_CAP
   uint32_t * const lbeg = kmers + KMER_CAP;                                       // KMER_CAP
   uint32_t * const llen = lbeg + KMER_CAP;                                        // KMER_CAP
+  uint32_t * const cum = llen + KMER_CAP;                                         // KMER_CAP + 1 (static index, flat stream)
   __shared__ int s_ncand, s_nk, s_T, s_K;
   __shared__ int s_wsum[RANK_THREADS / 32];
 
   int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NWARPS = RANK_THREADS / 32;
 
+  bool clean = false;   // the counters are all zero (left so by the previous shard's last scan)
   for (int qi = blockIdx.x; qi < nq; qi += gridDim.x) {
     int64_t const q = q0 + qi;
     const uint8_t * __restrict__ s = qs.sym + qs.off[q];
@@ -377,12 +388,15 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
       if (threadIdx.x == 0) { s_T = static_cast<int>(minmatches); }
     }
     // visits every counter >= thr of the current shard: f(count, local target)
-    auto scan_counters = [&](int nt, uint32_t thr, auto && f) {
+    // zero != 0: the counters are cleared behind the scan (the next shard then skips its clearing pass)
+    auto scan_counters = [&](int nt, uint32_t thr, int zero, auto && f) {
       int const nvec = (((nt + 1) >> 1) + 3) >> 2;
       uint32_t const below = thr > 0 ? ((thr - 1) | ((thr - 1) << 16)) : 0u;
-      const uint4 * __restrict__ cv = reinterpret_cast<const uint4 *>(counters);
+      uint4 * __restrict__ cv = reinterpret_cast<uint4 *>(counters);
+      if (zero != 0 && threadIdx.x == 0) { counters[(POST_PAD >> 2)] = 0; }   // where the padding entries of the lists land
       for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
         uint4 const x = cv[vi];
+        if (zero != 0) { cv[vi] = make_uint4(0u, 0u, 0u, 0u); }
         uint32_t const w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -399,7 +413,8 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
     for (int sh = 0; sh < nshards; sh++) {
       ShardDev const S = shards[sh];
       // 2. zero the counters; fetch the bounds of every k-mer's posting list in this shard
-      for (int i = threadIdx.x; i < COUNTER_WORDS; i += blockDim.x) { counters[i] = 0; }
+      if (!clean) { for (int i = threadIdx.x; i < COUNTER_WORDS; i += blockDim.x) { counters[i] = 0; } }
+      clean = false;
       for (int chunk = 0; chunk < nchunks; chunk++) {
       if (longq) {
         int const cn = nk > 0 ? min(KMER_CAP, nk - chunk * KMER_CAP) : 1;
@@ -452,9 +467,126 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
             atomicAdd(&counters[a >> 1], (a & 1) ? 0x10000u : 1u);
           }
         }
+      }
+#ifdef VSG_RANK_LEGACY
+      else if (flat != 0) {
+#else
+      else {
+#endif
+        // FLAT VECTOR STREAM.  The even and the odd sub-list of a k-mer are one contiguous run of 16-byte vectors, and
+        // the runs of all the query's k-mers, laid end to end, form one virtual stream of Vtot vectors.  Each warp
+        // takes a contiguous 1/16 of the stream and walks it 32 vectors per round — every lane always has a vector
+        // (a per-k-mer loop leaves most lanes idle on the second trip of a 36-vector sub-list and pays its set-up
+        // 243 times per shard).  Per run i, with c_i its position in the stream:
+        //   cum[i]  = c_i + n_i          where the run ends
+        //   lbeg[i] = first vector - c_i  so that stream position + lbeg = the vector's index in the shard's postings
+        //   llen[i] = c_i + na_i         positions below it hold even targets (increment 1), the rest odd ones (0x10000)
+        // A lane finds its first run by one binary search and then walks forward (runs average two rounds).
+        uint32_t Vtot;
+        {
+          // 3a. exclusive prefix sum of the run lengths (in vectors)
+          int const per = (np2 + RANK_THREADS - 1) / RANK_THREADS;   // <= 4
+          int const i0 = threadIdx.x * per;
+          uint32_t nn[KMER_CAP / RANK_THREADS], bb[KMER_CAP / RANK_THREADS];
+          uint32_t sum = 0;
+#pragma unroll
+          for (int u = 0; u < KMER_CAP / RANK_THREADS; u++) {
+            bool const in = u < per && i0 + u < np2;
+            nn[u] = in ? llen[i0 + u] : 0u;
+            bb[u] = in ? lbeg[i0 + u] : 0u;
+            sum += (nn[u] & 0xffffu) + (nn[u] >> 16);
+          }
+          uint32_t incl = sum;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) { uint32_t const o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) { incl += o; } }
+          if (lane == 31) { s_wsum[warp] = static_cast<int>(incl); }
+          __syncthreads();
+          uint32_t wbase = 0, total = 0;
+#pragma unroll
+          for (int w2 = 0; w2 < NWARPS; w2++) { uint32_t const v = static_cast<uint32_t>(s_wsum[w2]); if (w2 < warp) { wbase += v; } total += v; }
+          uint32_t c0 = wbase + incl - sum;
+#pragma unroll
+          for (int u = 0; u < KMER_CAP / RANK_THREADS; u++) {
+            if (u < per && i0 + u < np2) {
+              uint32_t const na = nn[u] & 0xffffu, n = na + (nn[u] >> 16);
+              lbeg[i0 + u] = (bb[u] >> 3) - c0;
+              llen[i0 + u] = c0 + na;
+              cum[i0 + u] = c0 + n;
+              c0 += n;
+            }
+          }
+          Vtot = total;
+          __syncthreads();
+        }
+        uint32_t const per_w = ((Vtot + NWARPS * 32 - 1) / (NWARPS * 32)) * 32;
+        uint32_t const wbeg = static_cast<uint32_t>(warp) * per_w;
+        uint32_t const wend = min(Vtot, wbeg + per_w);
+        if (wbeg < wend) {
+          constexpr int U = VSG_RANK_U;   // vectors (of 8 postings) held per lane
+          const uint4 * __restrict__ pbase = reinterpret_cast<const uint4 *>(S.post);
+          uint32_t const cnt_sa = static_cast<uint32_t>(__cvta_generic_to_shared(counters));
+          // the run holding this lane's first vector: the first whose end lies beyond it
+          uint32_t const v_first = min(wbeg + static_cast<uint32_t>(lane), wend - 1);
+          int lo = 0, hi = np2 - 1;
+          while (lo < hi) {
+            int const mid = (lo + hi) >> 1;
+            if (cum[mid] <= v_first) { lo = mid + 1; } else { hi = mid; }
+          }
+          // sa walks the run arrays as a shared-memory byte address of lbeg[s]; llen and cum lie KMER_CAP words further each
+          uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(lbeg + lo));
+          uint32_t ce = cum[lo];
+          // U loads per lane are issued back to back, then turned into counter updates; the other 31 warps of the SM
+          // cover the wait (VSG_RANK_ROLL refills each slot right after its use instead: measured equal).
+          uint4 cur[U];
+          uint32_t inc[U];
+          auto fetch = [&](int u, uint32_t vv) {
+            inc[u] = 0u;
+            if (vv < wend) {
+              while (vv >= ce) {
+                sa += 4u;
+                asm("ld.shared.u32 %0, [%1+%2];" : "=r"(ce) : "r"(sa), "n"(2 * KMER_CAP * 4));
+              }
+              uint32_t vb, sp;
+              asm("ld.shared.u32 %0, [%1];" : "=r"(vb) : "r"(sa));
+              asm("ld.shared.u32 %0, [%1+%2];" : "=r"(sp) : "r"(sa), "n"(KMER_CAP * 4));
+              cur[u] = __ldg(pbase + static_cast<uint32_t>(vb + vv));
+              inc[u] = vv < sp ? 1u : 0x10000u;
+            }
+          };
+          auto apply = [&](int u) {
+            if (inc[u] != 0u) {
+              uint32_t const w[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
+#pragma unroll
+              for (int k2 = 0; k2 < 4; k2++) {
+                // the postings ARE the byte offsets of their counter words
+                asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(cnt_sa + (w[k2] & 0xffffu)), "r"(inc[u]));
+                asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(cnt_sa + (w[k2] >> 16)), "r"(inc[u]));
+              }
+            }
+          };
+#if VSG_RANK_ROLL
+#pragma unroll
+          for (int u = 0; u < U; u++) { fetch(u, wbeg + 32u * u + static_cast<uint32_t>(lane)); }
+          for (uint32_t v0 = wbeg; v0 < wend; v0 += 32u * U) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+              apply(u);
+              fetch(u, v0 + 32u * (U + u) + static_cast<uint32_t>(lane));
+            }
+          }
+#else
+          for (uint32_t v0 = wbeg; v0 < wend; v0 += 32u * U) {
+#pragma unroll
+            for (int u = 0; u < U; u++) { fetch(u, v0 + 32u * u + static_cast<uint32_t>(lane)); }
+#pragma unroll
+            for (int u = 0; u < U; u++) { apply(u); }
+          }
+#endif
+        }
+#ifdef VSG_RANK_LEGACY
       } else {
-        // a warp takes one k-mer at a time: list a = its even targets (increment 1), list b = its odd targets
-        // (increment 0x10000)
+        // (A/B reference, VSG_RANK_FLAT=0) a warp takes one k-mer at a time: list a = its even targets (increment 1),
+        // list b = its odd targets (increment 0x10000)
         auto pair_len = [&](int li) -> uint32_t {
           uint32_t const na = llen[li] & 0xffffu, nb = llen[li] >> 16;
           return na > nb ? na : nb;
@@ -523,6 +655,9 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
           li = nli; base = nbase; have = nhave;
         }
       }
+#else
+      }
+#endif
       __syncthreads();
       }  // chunk
       int const nwords = (S.nt + 1) >> 1;
@@ -530,7 +665,7 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
       if (running) {
         // 4r. histogram of this shard's counts >= T, new T, then keys for counts >= new T only
         uint32_t const T0 = static_cast<uint32_t>(s_T);
-        scan_counters(S.nt, T0, [&](uint32_t c, int) { atomicAdd(&hist[c], 1u); });
+        scan_counters(S.nt, T0, 0, [&](uint32_t c, int) { atomicAdd(&hist[c], 1u); });
         __syncthreads();
         if (warp == 0) {
           int acc = 0, T = static_cast<int>(T0), K = -1;
@@ -558,10 +693,11 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
         int const K = s_K;
         if (level + K <= CAND_CAP) {
           // at most K targets (all shards so far) are >= T1, so at most K keys are appended here
-          scan_counters(S.nt, T1, [&](uint32_t c, int lt) {
+          scan_counters(S.nt, T1, VSG_RANK_ZFUSE, [&](uint32_t c, int lt) {
             int const t = S.t0 + lt;
             cand[atomicAdd(&s_ncand, 1)] = make_key(c, static_cast<uint32_t>(db.len[t]), static_cast<uint32_t>(t));
           });
+          clean = VSG_RANK_ZFUSE != 0;
           __syncthreads();
           continue;  // next shard
         }
@@ -702,7 +838,7 @@ rank_kernel(DevSeqs qs, int64_t q0, int nq, DevSeqs db, const ShardDev * __restr
   }
 }
 
-constexpr size_t RANK_SMEM = CAND_CAP * 8 + (COUNTER_WORDS + 3) * 4 + KMER_CAP * 4 * 3;
+constexpr size_t RANK_SMEM = CAND_CAP * 8 + (COUNTER_WORDS + 3) * 4 + KMER_CAP * 4 * 4 + 4;   // 114 708 B: two CTAs fit an SM's 227 KB
 
 }  // namespace vsg
 
@@ -1000,11 +1136,12 @@ int rank_enqueue(vsg_ctx * c, const vsg_index * ix, const vsg_seqset * queries, 
     if ((rc = c->rank_scratch.reserve(sizeof(uint32_t) * stride * static_cast<size_t>(grid))) != VSG_OK) { return rc; }
     d_scratch = static_cast<uint32_t *>(c->rank_scratch.p);
   }
+  static int const rank_flat = [] { const char * e = std::getenv("VSG_RANK_FLAT"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
   VSG_CUDA_OK(cudaEventRecord(c->ev[4], rs));
   rank_kernel<false><<<grid, RANK_THREADS, RANK_SMEM, rs>>>(
       queries->d, q0, static_cast<int>(nq), ix->db->d, static_cast<const ShardDev *>(ix->b_shards.p),
       static_cast<int>(ix->h_shards.size()), ix->k, mask_lower, minwordmatches, tophits, *d_seqno, *d_count, *d_n,
-      *d_status, d_scratch, stride, bitmap_words);
+      *d_status, d_scratch, stride, bitmap_words, rank_flat);
   count_launch();
   VSG_CUDA_OK(cudaEventRecord(c->ev[5], rs));
   c->rank_pending = true;
@@ -1244,7 +1381,7 @@ int cindex_rank_enqueue(vsg_ctx * c, CIndex * ix, const vsg_seqset * queries, in
   }
   rank_kernel<true><<<grid, RANK_THREADS, RANK_SMEM, c->stream>>>(
       queries->d, q0, static_cast<int>(nq), lens, static_cast<const ShardDev *>(ix->b_shards.p), nshards, ix->k, ix->mask_lower,
-      minwordmatches, tophits, *d_seqno, *d_count, *d_n, *d_status, d_scratch, stride, bitmap_words);
+      minwordmatches, tophits, *d_seqno, *d_count, *d_n, *d_status, d_scratch, stride, bitmap_words, 0);
   count_launch();
   return VSG_OK;
 }

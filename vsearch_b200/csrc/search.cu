@@ -60,6 +60,7 @@ struct SearchScratch {  // per host thread, see vsg_ctx::search_scratch
   size_t hits_cap = 0;
   std::vector<uint32_t> pq, pt, lq, lt;
   std::vector<int> pstate, px, lstate;
+  std::vector<int32_t> plead, lead_tmp;   // traceback on demand: each pair's group leader (index into the round's pair list) or -1
   std::vector<int64_t> ldest;
   std::vector<int16_t> a_score, l_score, t_score;
   std::vector<uint16_t> a_al, a_ma, a_mi, a_ga, l_al, l_ma, l_mi, l_ga, t_al, t_ma, t_mi, t_ga;
@@ -144,6 +145,23 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   double const opt_weak_id = (opts->id >= 0.0 && opts->weak_id > opts->id) ? opts->id : opts->weak_id;
   int64_t total_pairs = 0, total_cells = 0, aligned_pairs = 0, aligned_cells = 0;
   bool const lazy = opts->lazy != 0;
+  // Traceback on demand (align_ckpt.cuh, TbGate) needs the device's verdict on a group's first candidate to be the
+  // host's: that holds when search_acceptable_aligned reduces to its identity test, i.e. every optional
+  // post-alignment filter is at its default and no pair can be diverted to the caller's aligner.  VSG_TB_GATE=0 turns
+  // it off (A/B runs; the results do not depend on it).
+  // VSG_TB_GATE_FORCE=1 (tests): the device takes EVERY leader for accepted, so every follower the replay needs goes
+  // through the re-alignment below
+  bool const tb_force = [] { const char * e = std::getenv("VSG_TB_GATE_FORCE"); return e != nullptr && e[0] == '1'; }();
+  bool tb_gate = false;
+  {
+    vsg_search_opts d;
+    vsg_search_opts_default(&d);
+    const char * const e = std::getenv("VSG_TB_GATE");
+    tb_gate = (e == nullptr || e[0] != '0') && !lazy && !c->sp.fallback &&
+              opts->maxsubs == d.maxsubs && opts->maxgaps == d.maxgaps && opts->mincols == d.mincols && opts->maxdiffs == d.maxdiffs &&
+              opts->leftjust == 0 && opts->rightjust == 0 && opts->query_cov == d.query_cov && opts->target_cov == d.target_cov &&
+              opts->maxid == d.maxid && opts->mid == d.mid && opts->iddef >= 0 && opts->iddef <= 4 && opt_weak_id <= opt_id;
+  }
   for (int64_t q = 0; q < nq; q++) { counts[q] = 0; }
   if (seqcount == 0 || nq == 0) { if (work) { work[0] = work[1] = work[2] = work[3] = 0; } return VSG_OK; }
   if (tophits64 > 1024) { Error::set("vsg_search_batch: maxaccepts+maxrejects+8 > 1024 is not supported on the device ranker"); return VSG_EINVAL; }
@@ -192,6 +210,8 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   auto & pq = sc.pq; auto & pt = sc.pt;
   auto & pstate = sc.pstate;  // which state each pair belongs to
   auto & px = sc.px;          // which of the state's hits
+  auto & plead = sc.plead; auto & lead_tmp = sc.lead_tmp;
+  int64_t tb_redone = 0;
   // tail mode (see below): one device call resolves every remaining candidate of the few queries still active
   auto & lq = sc.lq; auto & lt = sc.lt; auto & lstate = sc.lstate; auto & ldest = sc.ldest;
   auto & l_score = sc.l_score; auto & t_score = sc.t_score;
@@ -286,10 +306,12 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
     t_init += ms(tp0, now());
     bool any = true;
     bool tail_mode = false;
+    bool gated_round = false;
     while (any) {
+      gated_round = false;
       tp0 = now();
       any = false;
-      pq.clear(); pt.clear(); pstate.clear(); px.clear();
+      pq.clear(); pt.clear(); pstate.clear(); px.clear(); plead.clear();
       // gather: run each active query's candidate loop up to its next align_delayed (searchcore.cpp:915-954)
       if (lazy) {
         // same decisions, alignments on demand: open the group the reference would hand to search16,
@@ -379,9 +401,15 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
         // align_delayed's search16 call: every not-yet-finalized, not pre-rejected hit
         int const strand = static_cast<int>(si / static_cast<size_t>(bn));
         int64_t const ql = static_cast<int64_t>(si % static_cast<size_t>(bn));
+        // traceback on demand (align_ckpt.cuh): if accepting the group's first candidate ends this query's search,
+        // the others are walked back only when that candidate turns out not to be accepted
+        bool const gate_group = tb_gate && (S.accepts + 1 >= maxaccepts);
+        int32_t leader = -1;
         for (int x = S.finalized; x < S.hit_count; x++) {
           Hit const & h = hits[static_cast<size_t>(S.hit_base) + x];
           if (!h.rejected) {
+            plead.push_back(gate_group ? leader : -1);
+            if (leader < 0) { leader = static_cast<int32_t>(pq.size()); }
             pq.push_back(static_cast<uint32_t>(strand == 0 ? q0 + b0 + ql : ql));
             pt.push_back(static_cast<uint32_t>(h.target));
             pstate.push_back(static_cast<int>(si));
@@ -398,7 +426,8 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
       // pairs of the plus strand index `queries`, those of the minus strand index rc_set: two calls
       // (states are ordered plus first, minus second, so pairs are too)
       auto device_align = [&](size_t n, const uint32_t * Q, const uint32_t * T, const int * state_of,
-                              int16_t * o_sc, uint16_t * o_al, uint16_t * o_ma, uint16_t * o_mi, uint16_t * o_ga, int32_t * o_tr) -> int {
+                              int16_t * o_sc, uint16_t * o_al, uint16_t * o_ma, uint16_t * o_mi, uint16_t * o_ga, int32_t * o_tr,
+                              const int32_t * lead) -> int {
         size_t split = n;
         if (nstrands == 2) {
           split = 0;
@@ -408,8 +437,16 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
           size_t const lo = part == 0 ? 0 : split, hi = part == 0 ? split : n;
           if (hi <= lo) { continue; }
           const vsg_seqset * qset = part == 0 ? queries : rc_set;
-          int const r = vsg_align_pairs(c, qset, db, static_cast<int64_t>(hi - lo), Q + lo, T + lo,
-                                        o_sc + lo, o_al + lo, o_ma + lo, o_mi + lo, o_ga + lo, o_tr + 4 * lo, nullptr, 0, nullptr);
+          const int32_t * lead_part = nullptr;
+          if (lead != nullptr) {
+            // leaders as indices into this part's own pair list (a group never straddles the strands)
+            lead_tmp.assign(lead + lo, lead + hi);
+            if (lo > 0) { for (auto & v : lead_tmp) { if (v >= 0) { v -= static_cast<int32_t>(lo); } } }
+            lead_part = lead_tmp.data();
+          }
+          int const r = align_pairs_gated(c, qset, db, static_cast<int64_t>(hi - lo), Q + lo, T + lo,
+                                          o_sc + lo, o_al + lo, o_ma + lo, o_mi + lo, o_ga + lo, o_tr + 4 * lo, nullptr, 0, nullptr,
+                                          lead_part, tb_force ? -1.0 : 100.0 * opt_id + 1e-7, opts->iddef);
           if (r != VSG_OK) { return r; }
         }
         return VSG_OK;
@@ -463,7 +500,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
         size_t const nc = static_cast<size_t>(ncache);
         t_score.resize(nc); t_al.resize(nc); t_ma.resize(nc); t_mi.resize(nc); t_ga.resize(nc); t_tr.resize(nc * 4);
         int const r = device_align(nl, lq.data(), lt.data(), lstate.data(), l_score.data(), l_al.data(), l_ma.data(),
-                                   l_mi.data(), l_ga.data(), l_tr.data());
+                                   l_mi.data(), l_ga.data(), l_tr.data(), nullptr);
         if (r != VSG_OK) { return r; }
         for (size_t k = 0; k < nl; k++) {
           if (ldest[k] >= 0) {
@@ -479,8 +516,9 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
         al_pairs += static_cast<int64_t>(nl);
         tail_mode = true;
       } else {
+        gated_round = tb_gate && !lazy && plead.size() == np;
         int const r = device_align(np, pq.data(), pt.data(), pstate.data(), a_score.data(), a_al.data(), a_ma.data(),
-                                   a_mi.data(), a_ga.data(), a_tr.data());
+                                   a_mi.data(), a_ga.data(), a_tr.data(), gated_round ? plead.data() : nullptr);
         if (r != VSG_OK) { return r; }
         al_pairs += static_cast<int64_t>(np);
       }
@@ -510,6 +548,15 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
             Hit & h = hits[static_cast<size_t>(S.hit_base) + x];
             if (h.rejected) { S.rejects++; continue; }
             int64_t fb[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            if (gated_round && plead[i] >= 0 && a_al[i] == 0xffffu && a_ma[i] == 0xffffu && a_mi[i] == 0xffffu) {
+              // its walk was skipped because the device took the group's leader for accepted, yet the replay is here:
+              // the two verdicts differ (a borderline identity); align this pair now
+              const vsg_seqset * qset = strand == 0 ? queries : rc_set;
+              int const r = vsg_align_pairs(c, qset, db, 1, &pq[i], &pt[i], &a_score[i], &a_al[i], &a_ma[i], &a_mi[i], &a_ga[i],
+                                            &a_tr[4 * i], nullptr, 0, nullptr);
+              if (r != VSG_OK) { return r; }
+              tb_redone++;
+            }
             bool const diverted = (a_score[i] == VSG_SCORE_SENTINEL);
             if (diverted) {
               // the reference's LinearMemoryAligner path (searchcore.cpp:806-832), host side of the boundary
@@ -581,8 +628,8 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
     t_join += ms(tp0, now());
   }
   if (trace) {
-    std::fprintf(stderr, "[vsg trace] batch@%lld: rank %.1f init %.1f gather %.1f align %.1f replay %.1f join %.1f ms; done at %.1f ms\n",
-                 static_cast<long long>(b0), t_rank, t_init, t_gather, t_align, t_replay, t_join, ms(t_call0, now()));
+    std::fprintf(stderr, "[vsg trace] batch@%lld: rank %.1f init %.1f gather %.1f align %.1f replay %.1f join %.1f ms; done at %.1f ms; %lld skipped walks redone\n",
+                 static_cast<long long>(b0), t_rank, t_init, t_gather, t_align, t_replay, t_join, ms(t_call0, now()), static_cast<long long>(tb_redone));
   }
   return VSG_OK;
   };

@@ -510,7 +510,8 @@ void launch_ckpt(vsg_ctx * c, int R, bool general, const DevSeqs & qs, const Dev
   }
 }
 
-int launch_tb_ckpt_tasks(vsg_ctx * c, int R, bool general, const DevSeqs & qs, const DevSeqs & ts, const FastTask * d_tasks, int n)
+int launch_tb_ckpt_tasks(vsg_ctx * c, int R, bool general, const DevSeqs & qs, const DevSeqs & ts, const FastTask * d_tasks, int n,
+                         const TbGate & gate)
 {
   // a grid that fills the device once (the kernel hands further pairs out itself), fewer blocks for small calls
   int rc;
@@ -518,7 +519,8 @@ int launch_tb_ckpt_tasks(vsg_ctx * c, int R, bool general, const DevSeqs & qs, c
   VSG_CUDA_OK(cudaMemsetAsync(c->ticket.p, 0, sizeof(int), c->stream));
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-  int const nthr = 2 * n;
+  int const nthr = gate.ids != nullptr ? gate.nids : 2 * n;
+  if (nthr == 0) { return VSG_OK; }
   int const want = (nthr + TB_CK_THREADS - 1) / TB_CK_THREADS;
   static int const refill = [] { const char * e = std::getenv("VSG_TB_REFILL"); return e != nullptr ? std::atoi(e) : 0; }();
   int const tbase = refill > 0 ? 0 : nthr;   // >= the number of pairs: every thread does its own pair only
@@ -529,7 +531,7 @@ int launch_tb_ckpt_tasks(vsg_ctx * c, int R, bool general, const DevSeqs & qs, c
     int const blocks = refill > 0 ? std::min(want, std::max(1, per_sm) * sms * refill) : want;
     traceback_ckpt_tasks_kernel<8><<<blocks, TB_CK_THREADS, tb_ck_smem(8), c->stream>>>(
         c->sp2, qs, ts, d_tasks, n, R, general ? 1 : 0, static_cast<const uint2 *>(c->dir.p), static_cast<const uint2 *>(c->bnd.p),
-        static_cast<int32_t *>(c->stats.p), static_cast<int *>(c->ticket.p), tbase);
+        static_cast<int32_t *>(c->stats.p), static_cast<int *>(c->ticket.p), tbase, gate);
   } else {
     cudaFuncSetAttribute(traceback_ckpt_tasks_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tb_ck_smem(16)));
     int per_sm = 1;
@@ -537,7 +539,7 @@ int launch_tb_ckpt_tasks(vsg_ctx * c, int R, bool general, const DevSeqs & qs, c
     int const blocks = refill > 0 ? std::min(want, std::max(1, per_sm) * sms * refill) : want;
     traceback_ckpt_tasks_kernel<16><<<blocks, TB_CK_THREADS, tb_ck_smem(16), c->stream>>>(
         c->sp2, qs, ts, d_tasks, n, R, general ? 1 : 0, static_cast<const uint2 *>(c->dir.p), static_cast<const uint2 *>(c->bnd.p),
-        static_cast<int32_t *>(c->stats.p), static_cast<int *>(c->ticket.p), tbase);
+        static_cast<int32_t *>(c->stats.p), static_cast<int *>(c->ticket.p), tbase, gate);
   }
   count_launch();
   return VSG_OK;
@@ -571,6 +573,19 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
                                int16_t * score, uint16_t * aligned, uint16_t * matches,
                                uint16_t * mismatches, uint16_t * gaps, int32_t * trims,
                                char * cigar_buf, int64_t cigar_cap, int64_t * cigar_off)
+{
+  return vsg::align_pairs_gated(c, queries, targets, npairs, qidx, tidx, score, aligned, matches, mismatches, gaps, trims,
+                                cigar_buf, cigar_cap, cigar_off, nullptr, 0.0, 2);
+}
+
+// leader_of (optional, npairs entries, statistics-only calls): traceback on demand, see align_ckpt.cuh (TbGate).  A pair
+// whose walk was skipped comes back with aligned = matches = mismatches = 0xffff.
+int vsg::align_pairs_gated(vsg_ctx * c, const vsg_seqset * queries, const vsg_seqset * targets,
+                           int64_t npairs, const uint32_t * qidx, const uint32_t * tidx,
+                           int16_t * score, uint16_t * aligned, uint16_t * matches,
+                           uint16_t * mismatches, uint16_t * gaps, int32_t * trims,
+                           char * cigar_buf, int64_t cigar_cap, int64_t * cigar_off,
+                           const int32_t * leader_of, double gate_threshold, int gate_iddef)
 {
   if (c == nullptr || queries == nullptr || targets == nullptr || npairs < 0 ||
       (npairs > 0 && (qidx == nullptr || tidx == nullptr || score == nullptr))) {
@@ -781,6 +796,47 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
       VSG_CUDA_OK(cudaMemcpyAsync(c->tasks_exact.p, hp + fb, eb, cudaMemcpyHostToDevice, c->stream));
     }
   }
+  // traceback on demand: per checkpoint run, the pair ids of the leaders (and ungated pairs) and of the followers
+  bool const gated = leader_of != nullptr && !want_cigar && !plans.empty();
+  struct GateRun { size_t lead_first, lead_count, foll_first, foll_count; };
+  std::vector<std::vector<GateRun>> gate_runs;
+  int const * d_gate_ids = nullptr;
+  int32_t const * d_leader = nullptr;
+  if (gated) {
+    std::vector<int> ids;
+    ids.reserve(static_cast<size_t>(npairs));
+    gate_runs.resize(plans.size());
+    for (size_t ci = 0; ci < plans.size(); ci++) {
+      for (auto const & run : plans[ci].runs) {
+        GateRun g{ids.size(), 0, 0, 0};
+        if (run.ckpt) {
+          for (int pass = 0; pass < 2; pass++) {
+            if (pass == 1) { g.lead_count = ids.size() - g.lead_first; g.foll_first = ids.size(); }
+            for (int k = 0; k < run.count; k++) {
+              FastTask const & ft = all_fast[run.first + static_cast<size_t>(k)];
+              for (int half = 0; half < 2; half++) {
+                int32_t const slot = half ? ft.out_hi : ft.out_lo;
+                if (slot < 0) { continue; }
+                bool const follower = leader_of[slot] >= 0;
+                if (follower == (pass == 1)) { ids.push_back(2 * k + half); }
+              }
+            }
+          }
+          g.foll_count = ids.size() - g.foll_first;
+        }
+        gate_runs[ci].push_back(g);
+      }
+    }
+    if ((rc = c->gate.reserve(sizeof(int) * (ids.size() + static_cast<size_t>(npairs)) + 64)) != VSG_OK) { return rc; }
+    int * const dg = static_cast<int *>(c->gate.p);
+    // pageable sources: both copies are staged before cudaMemcpyAsync returns
+    if (!ids.empty()) { VSG_CUDA_OK(cudaMemcpyAsync(dg, ids.data(), sizeof(int) * ids.size(), cudaMemcpyHostToDevice, c->stream)); }
+    VSG_CUDA_OK(cudaMemcpyAsync(dg + ids.size(), leader_of, sizeof(int32_t) * static_cast<size_t>(npairs), cudaMemcpyHostToDevice, c->stream));
+    d_gate_ids = dg;
+    d_leader = dg + ids.size();
+    // "not computed" everywhere until a kernel says otherwise
+    VSG_CUDA_OK(cudaMemsetAsync(c->stats.p, 0xff, sizeof(int32_t) * VSG_STAT_WORDS * static_cast<size_t>(npairs), c->stream));
+  }
   // events: 3 per chunk
   while (c->ev_pool.size() < 3 * plans.size()) {
     cudaEvent_t e;
@@ -807,9 +863,27 @@ extern "C" int vsg_align_pairs(vsg_ctx * c, const vsg_seqset * queries, const vs
     }
     VSG_CUDA_OK(cudaEventRecord(c->ev_pool[3 * ci + 1], c->stream));
     if (!want_cigar) {
-      for (auto const & run : pl.runs) {
+      TbGate const no_gate{nullptr, 0, nullptr, 0, 2, 0.0};
+      if (gated) {
+        // phase 1: leaders and ungated pairs of every checkpoint run (their verdicts must be in before any follower looks)
+        for (size_t ri = 0; ri < pl.runs.size(); ri++) {
+          auto const & run = pl.runs[ri];
+          if (!run.ckpt) { continue; }
+          GateRun const & g = gate_runs[ci][ri];
+          TbGate const g1{d_gate_ids + g.lead_first, static_cast<int>(g.lead_count), d_leader, 1, gate_iddef, gate_threshold};
+          if ((rc = launch_tb_ckpt_tasks(c, run.R, run.general, queries->d, targets->d, d_fast + run.first, run.count, g1)) != VSG_OK) { return rc; }
+        }
+      }
+      for (size_t ri = 0; ri < pl.runs.size(); ri++) {
+        auto const & run = pl.runs[ri];
         if (run.ckpt) {
-          if ((rc = launch_tb_ckpt_tasks(c, run.R, run.general, queries->d, targets->d, d_fast + run.first, run.count)) != VSG_OK) { return rc; }
+          if (gated) {
+            GateRun const & g = gate_runs[ci][ri];
+            TbGate const g2{d_gate_ids + g.foll_first, static_cast<int>(g.foll_count), d_leader, 2, gate_iddef, gate_threshold};
+            if ((rc = launch_tb_ckpt_tasks(c, run.R, run.general, queries->d, targets->d, d_fast + run.first, run.count, g2)) != VSG_OK) { return rc; }
+            continue;
+          }
+          if ((rc = launch_tb_ckpt_tasks(c, run.R, run.general, queries->d, targets->d, d_fast + run.first, run.count, no_gate)) != VSG_OK) { return rc; }
           continue;
         }
         int const nthr = 2 * run.count;

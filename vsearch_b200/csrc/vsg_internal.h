@@ -100,6 +100,15 @@ struct PinBuf {
 
 void count_launch(int n = 1);
 
+// vsg_align_pairs with traceback on demand (align_ckpt.cuh, TbGate): leader_of[k] = index of pair k's group leader in
+// this call, or -1; threshold = 100 * --id (+ margin); skipped pairs return aligned = matches = mismatches = 0xffff
+int align_pairs_gated(vsg_ctx * c, const vsg_seqset * queries, const vsg_seqset * targets,
+                      int64_t npairs, const uint32_t * qidx, const uint32_t * tidx,
+                      int16_t * score, uint16_t * aligned, uint16_t * matches,
+                      uint16_t * mismatches, uint16_t * gaps, int32_t * trims,
+                      char * cigar_buf, int64_t cigar_cap, int64_t * cigar_off,
+                      const int32_t * leader_of, double gate_threshold, int gate_iddef);
+
 }  // namespace vsg
 
 struct vsg_seqset {
@@ -122,7 +131,7 @@ struct vsg_ctx {
   bool fast_disabled = false;  // VSG_DISABLE_FAST=1 (tests force the exact kernel)
   // scratch
   vsg::DevBuf dir, bnd, he, cigar_scratch, cigar_dense, stats, tasks_fast, tasks_exact, pairs,
-      cigar_len, cigar_offs, cub_tmp, rank_tmp, rank_scratch, pre_flags, ticket;
+      cigar_len, cigar_offs, cub_tmp, rank_tmp, rank_scratch, pre_flags, ticket, gate;
   vsg::PinBuf h_tasks, h_stats;
   size_t dir_budget = (size_t)64 << 30;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
