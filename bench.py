@@ -878,7 +878,11 @@ def usearch_workload(args, rank, world, local):
                            "masking": args.masking, "wordlength": K, "maxaccepts": MAXACC, "maxrejects": MAXREJ,
                            "index_build_ms_per_gpu": round(index_build_ms, 1),
                            "parallelism": f"query-sharded x{world}, DB NCCL-broadcast",
-                           "l2": "per-step working set (index 300 MB + direction blocks > 10 GB) exceeds the 126 MB L2"},
+                           "l2": "per-step working set (index 300 MB + checkpoints > 10 GB) exceeds the 126 MB L2",
+                           "traceback": ("every pair's forward DP is computed; the walk back of a group's other candidates is skipped "
+                                         "when its first candidate is accepted and ends the query's search (never examined by "
+                                         "align_delayed, searchcore.cpp:780-880); identical hit tables; VSG_TB_GATE=0 walks all"
+                                         if os.environ.get("VSG_TB_GATE", "1") != "0" else "every pair walked back (VSG_TB_GATE=0)")},
                 "queries_per_s": args.batch * world * args.steps / (ms_dev * 1e-3),
                 "pairs_per_s": float(work_dev[0]) / (ms_dev * 1e-3),
                 "hit_fraction_last_step": hits / args.batch,
