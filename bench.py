@@ -885,6 +885,7 @@ def usearch_workload(args, rank, world, local):
                                          if os.environ.get("VSG_TB_GATE", "1") != "0" else "every pair walked back (VSG_TB_GATE=0)")},
                 "queries_per_s": args.batch * world * args.steps / (ms_dev * 1e-3),
                 "pairs_per_s": float(work_dev[0]) / (ms_dev * 1e-3),
+                "walks_skipped_fraction": (float(prof.tb_skipped) / float(work_dev[0])) if work_dev[0] > 0 else 0.0,
                 "hit_fraction_last_step": hits / args.batch,
                 "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": qbytes,
                         "d2h_bytes_per_step": rbytes, "ms_per_step": ms_e2e / args.steps,

@@ -138,6 +138,7 @@ typedef struct vsg_profile {
   float traceback_ms;
   float rank_ms;
   float reserved;
+  int64_t tb_skipped;   /* pairs whose walk back was skipped by traceback on demand (vsg_search_batch; their DP was computed) */
 } vsg_profile;
 int vsg_profile_reset(vsg_ctx * ctx);
 int vsg_profile_get(vsg_ctx * ctx, vsg_profile * out);

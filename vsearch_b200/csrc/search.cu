@@ -665,6 +665,7 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
   for (int t = 0; t < nthreads; t++) {
     vsg_ctx * wc = c->children[static_cast<size_t>(t)];
     c->prof_cells += wc->prof_cells; c->prof_fast += wc->prof_fast; c->prof_exact += wc->prof_exact;
+    c->prof_tb_skipped += wc->prof_tb_skipped;
     c->prof_fwd_launches += wc->prof_fwd_launches;
     c->prof_fwd_ms += wc->prof_fwd_ms; c->prof_tb_ms += wc->prof_tb_ms; c->prof_rank_ms += wc->prof_rank_ms;
     vsg_profile_reset(wc);
@@ -846,6 +847,7 @@ extern "C" int vsg_allpairs(vsg_ctx * c, const vsg_seqset * set, int64_t row0, i
   for (int t = 0; t < nthreads; t++) {
     vsg_ctx * wc = c->children[static_cast<size_t>(t)];
     c->prof_cells += wc->prof_cells; c->prof_fast += wc->prof_fast; c->prof_exact += wc->prof_exact;
+    c->prof_tb_skipped += wc->prof_tb_skipped;
     c->prof_fwd_launches += wc->prof_fwd_launches;
     c->prof_fwd_ms += wc->prof_fwd_ms; c->prof_tb_ms += wc->prof_tb_ms; c->prof_rank_ms += wc->prof_rank_ms;
     vsg_profile_reset(wc);

@@ -970,6 +970,7 @@ int vsg::align_pairs_gated(vsg_ctx * c, const vsg_seqset * queries, const vsg_se
   int64_t cpos = 0;
   for (int64_t k = 0; k < npairs; k++) {
     int32_t const * s = hs + static_cast<size_t>(k) * VSG_STAT_WORDS;
+    if (gated && leader_of[k] >= 0 && s[VSG_STAT_ALIGNED] == -1 && s[VSG_STAT_MATCHES] == -1) { c->prof_tb_skipped++; }
     score[k] = static_cast<int16_t>(s[VSG_STAT_SCORE]);
     if (aligned != nullptr) { aligned[k] = static_cast<uint16_t>(s[VSG_STAT_ALIGNED]); }
     if (matches != nullptr) { matches[k] = static_cast<uint16_t>(s[VSG_STAT_MATCHES]); }
@@ -1056,7 +1057,7 @@ extern "C" int vsg_measure_int_peak(vsg_ctx * c, double * packed_lane_ops_per_s)
 extern "C" int vsg_profile_reset(vsg_ctx * c)
 {
   if (c == nullptr) { return VSG_EINVAL; }
-  c->prof_cells = c->prof_fast = c->prof_exact = c->prof_fwd_launches = 0;
+  c->prof_cells = c->prof_fast = c->prof_exact = c->prof_fwd_launches = c->prof_tb_skipped = 0;
   c->prof_fwd_ms = c->prof_tb_ms = c->prof_rank_ms = 0.f;
   return VSG_OK;
 }
@@ -1068,5 +1069,6 @@ extern "C" int vsg_profile_get(vsg_ctx * c, vsg_profile * out)
   out->fwd_launches = c->prof_fwd_launches;
   out->fwd_ms = c->prof_fwd_ms; out->traceback_ms = c->prof_tb_ms; out->rank_ms = c->prof_rank_ms;
   out->reserved = 0.f;
+  out->tb_skipped = c->prof_tb_skipped;
   return VSG_OK;
 }

@@ -136,7 +136,7 @@ struct vsg_ctx {
   size_t dir_budget = (size_t)64 << 30;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // cumulative profile since the last vsg_profile_reset (kernel times from cudaEvents on `stream`)
-  int64_t prof_cells = 0, prof_fast = 0, prof_exact = 0, prof_fwd_launches = 0;
+  int64_t prof_cells = 0, prof_fast = 0, prof_exact = 0, prof_fwd_launches = 0, prof_tb_skipped = 0;
   float prof_fwd_ms = 0.f, prof_tb_ms = 0.f, prof_rank_ms = 0.f;
   bool rank_pending = false;
   std::vector<cudaEvent_t> ev_pool;  // 3 per chunk of an align call

@@ -50,7 +50,7 @@ class SearchOpts(C.Structure):
 class Profile(C.Structure):
     _fields_ = [("cells", C.c_int64), ("fast_pairs", C.c_int64), ("exact_pairs", C.c_int64),
                 ("fwd_launches", C.c_int64), ("fwd_ms", C.c_float), ("traceback_ms", C.c_float),
-                ("rank_ms", C.c_float), ("reserved", C.c_float)]
+                ("rank_ms", C.c_float), ("reserved", C.c_float), ("tb_skipped", C.c_int64)]
 
 
 class SearchResult(C.Structure):
