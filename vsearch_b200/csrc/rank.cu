@@ -878,6 +878,13 @@ static int build_dense_shard(vsg_ctx * c, vsg_index * ix, int sh, int t0, int nt
   size_t const bitmap_bytes = std::max<size_t>(hashsize / 8, 4);
   size_t const nlists = 2 * hashsize;   // even and odd targets of every k-mer
   int rc;
+  // list offsets are 32-bit: a shard's postings (at most one per nucleotide) plus the padding of its lists must fit
+  int64_t nuc = 0;
+  for (int i = 0; i < nt; i++) { nuc += db->h_len[static_cast<size_t>(t0) + static_cast<size_t>(i)]; }
+  if (nuc + 7 * static_cast<int64_t>(nlists) >= (static_cast<int64_t>(1) << 32) - 64) {
+    Error::set("vsg_index_create: a shard of 32766 targets holds 2^32 nucleotides or more");
+    return VSG_EINVAL;
+  }
   DevBuf & bs = ix->b_start[static_cast<size_t>(sh)];
   if ((rc = bs.reserve(sizeof(uint32_t) * (nlists + 1))) != VSG_OK) { return rc; }
   VSG_CUDA_OK(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * (nlists + 1), c->stream));
