@@ -213,11 +213,14 @@ typedef struct vsg_search_opts {
   int32_t qmask_dust;     /* --qmask dust with --strand both: the caller has DUST-masked `queries`
                              (vsg_seqset_dust); the reverse complements made inside the call are masked
                              on their own, as search_batch_worker_fn does per strand (core/search.cpp:437-449) */
-  int32_t reserved0;
+  int32_t unoise;         /* --cluster_unoise acceptance (searchcore.cpp:700-717): a hit that passes the filters is accepted
+                             iff it has no mismatch or query abundance / target abundance <= 1 / 2^(unoise_alpha * mismatches + 1),
+                             instead of the --id test; needs query_sizes / target_sizes */
   const int64_t * query_sizes;   /* abundance of query q0+i at [i]; NULL = 1 everywhere (db.getabundance / qsize) */
   const int64_t * target_sizes;  /* abundance of target t at [t];   NULL = 1 everywhere                     */
   const int64_t * query_labels;  /* --self: label identities, [i] for query q0+i resp. [t] for target t; two  */
   const int64_t * target_labels; /*         sequences carry the same header iff their identities are equal  */
+  double unoise_alpha;    /* --unoise_alpha (2.0) */
 } vsg_search_opts;
 
 typedef struct vsg_search_result {

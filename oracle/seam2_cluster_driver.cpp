@@ -46,6 +46,7 @@ int main(int argc, char ** argv)
     else if (k == "minsl") { p.opt_minsl = std::atof(v); }
     else if (k == "maxqt") { p.opt_maxqt = std::atof(v); }
     else if (k == "mid") { p.opt_mid = std::atof(v); }
+    else if (k == "unoise_alpha") { p.opt_cluster_unoise = const_cast<char *>("unoise"); p.opt_unoise_alpha = std::atof(v); }
     else if (k == "chunk") { chunk = std::atoi(v); }
     else { std::fprintf(stderr, "unknown key %s\n", k.c_str()); return 2; }
   }
@@ -56,7 +57,13 @@ int main(int argc, char ** argv)
     std::ifstream in(argv[1]);
     if (!in) { std::fprintf(stderr, "cannot open %s\n", argv[1]); return 2; }
     std::string line, head, seq;
-    auto flush = [&]() { if (!head.empty()) { db.add(false, head.c_str(), seq.c_str(), nullptr, head.size(), seq.size(), 1); } };
+    auto flush = [&]() {
+      if (head.empty()) { return; }
+      int64_t size = 1;   // ";size=N" in the header = the abundance (what --sizein reads)
+      size_t const at = head.find(";size=");
+      if (at != std::string::npos) { size = std::max<int64_t>(1, std::atoll(head.c_str() + at + 6)); }
+      db.add(false, head.c_str(), seq.c_str(), nullptr, head.size(), seq.size(), size);
+    };
     while (std::getline(in, line)) {
       if (!line.empty() && line.back() == '\r') { line.pop_back(); }
       if (line.empty()) { continue; }

@@ -106,6 +106,7 @@ int main(int argc, char ** argv)
     else if (k == "maxdiffs") { p.opt_maxdiffs = std::atoll(v); }
     else if (k == "leftjust") { p.opt_leftjust = std::atoll(v); }
     else if (k == "rightjust") { p.opt_rightjust = std::atoll(v); }
+    else if (k == "unoise_alpha") { p.opt_cluster_unoise = const_cast<char *>("unoise"); p.opt_unoise_alpha = std::atof(v); }
     else if (k == "match") { p.opt_match = std::atoll(v); }
     else if (k == "mismatch") { p.opt_mismatch = std::atoll(v); }
     else if (k == "gapopen_i") { p.opt_gap_open_query_interior = p.opt_gap_open_target_interior = std::atoll(v); }

@@ -182,7 +182,6 @@ auto cluster_session_init(struct cluster_session_s * cs, struct Parameters const
   cs->parameters = &p; cs->dbindex = &dbindex; cs->db = &db;
   cs->seqcount = static_cast<int>(db.getsequencecount());
   if (p.opt_strand) { fatal("GPU cluster session: --strand both is not offered on this path"); }
-  if (p.opt_cluster_unoise != nullptr) { fatal("GPU cluster session: --cluster_unoise acceptance is not offered on this path"); }
   if (p.opt_sizeorder) { fatal("GPU cluster session: --sizeorder is not offered on this path"); }
 
   vsg_scoring sco;
@@ -226,6 +225,7 @@ auto cluster_session_init(struct cluster_session_s * cs, struct Parameters const
   o.maxid = p.opt_maxid; o.mid = p.opt_mid; o.query_cov = p.opt_query_cov; o.target_cov = p.opt_target_cov;
   o.maxsubs = p.opt_maxsubs; o.maxgaps = p.opt_maxgaps; o.mincols = p.opt_mincols; o.maxdiffs = p.opt_maxdiffs;
   o.leftjust = p.opt_leftjust != 0 ? 1 : 0; o.rightjust = p.opt_rightjust != 0 ? 1 : 0;
+  o.unoise = (p.opt_cluster_unoise != nullptr) ? 1 : 0; o.unoise_alpha = p.opt_unoise_alpha;
   o.maxqsize = p.opt_maxqsize; o.mintsize = p.opt_mintsize;
   o.minsizeratio = p.opt_minsizeratio; o.maxsizeratio = p.opt_maxsizeratio;
   o.self = p.opt_self != 0 ? 1 : 0;

@@ -222,7 +222,6 @@ auto search_batch(struct Parameters const & parameters,
   // the library path does not clamp the limits to the database size (search.cpp:523-531): with a limit of
   // zero search_onequery's loop never runs (searchcore.cpp:915-918)
   if (p.opt_maxaccepts <= 0 || p.opt_maxrejects <= 0) { return; }
-  if (p.opt_cluster_unoise != nullptr) { fatal("GPU search_batch: --cluster_unoise acceptance is not offered on this path"); }
   if (p.opt_qmask == Masking::dust && p.opt_hardmask) { fatal("GPU search_batch: --qmask dust with --hardmask is not offered on this path"); }
 
   Mirror & m = mirror_of(p, dbindex, db);
@@ -258,6 +257,7 @@ auto search_batch(struct Parameters const & parameters,
   o.maxid = p.opt_maxid; o.mid = p.opt_mid; o.query_cov = p.opt_query_cov; o.target_cov = p.opt_target_cov;
   o.maxsubs = p.opt_maxsubs; o.maxgaps = p.opt_maxgaps; o.mincols = p.opt_mincols; o.maxdiffs = p.opt_maxdiffs;
   o.leftjust = p.opt_leftjust != 0 ? 1 : 0; o.rightjust = p.opt_rightjust != 0 ? 1 : 0;
+  o.unoise = (p.opt_cluster_unoise != nullptr) ? 1 : 0; o.unoise_alpha = p.opt_unoise_alpha;
   o.maxqsize = p.opt_maxqsize; o.mintsize = p.opt_mintsize;
   o.minsizeratio = p.opt_minsizeratio; o.maxsizeratio = p.opt_maxsizeratio;
   if (p.opt_idprefix > 2147483647 || p.opt_idsuffix > 2147483647) { fatal("GPU search_batch: --idprefix/--idsuffix out of range"); }

@@ -97,6 +97,9 @@ CASES = [
     ["id=0.8", "maxaccepts=2", "maxrejects=6", "infinite_ext=ql,tr", "strand=1"],
     ["id=0.8", "maxaccepts=0", "maxrejects=8"],                                         # library path: a zero limit finds nothing
     ["id=0.9", "maxaccepts=1", "maxrejects=32", "wordlength=7", "threads=3"],
+    ["id=0.8", "maxaccepts=3", "maxrejects=8", "unoise_alpha=2.0"],                     # --cluster_unoise acceptance (searchcore.cpp:700-717)
+    ["id=0.8", "maxaccepts=2", "maxrejects=16", "unoise_alpha=0.3", "strand=1"],
+    ["id=0.9", "maxaccepts=2", "maxrejects=16", "wordlength=12"],                       # sparse index through the shim
 ]
 
 
@@ -144,7 +147,7 @@ def _reads(tmp_path):
             s = s[:100] + b"ACACACACACACACACACACACACACACACACACAC" + s[100:]   # DUST bait
         if i % 97 == 11:
             s = s[:50] + b"NRY" + s[53:]                                        # IUPAC -> the general kernel
-        recs.append([f"r{i}", s.decode()])
+        recs.append([f"r{i};size={int(rng.integers(1, 200))}", s.decode()])
     path = str(tmp_path / "reads.fasta")
     _write_fasta(path, recs)
     return path
@@ -157,6 +160,8 @@ def _reads(tmp_path):
     ["id=0.95", "threads=32", "chunk=257", "maxrejects=16"],   # ranges that do not line up with the rounds
     ["id=0.9", "threads=128", "chunk=700", "qmask=none", "maxaccepts=2", "iddef=1"],
     ["id=0.97", "threads=4", "chunk=400", "minsl=0.9", "mid=0.9"],
+    ["id=0.9", "threads=16", "chunk=300", "unoise_alpha=2.0"],   # --cluster_unoise acceptance: abundance skew instead of --id
+    ["id=0.9", "threads=1", "chunk=0", "unoise_alpha=0.5", "maxaccepts=2"],
 ])
 def test_cluster_session_shim_equals_the_reference(tmp_path, case):
     reads = _reads(tmp_path)

@@ -281,7 +281,7 @@ int session_rounds(vsg_cluster_session & s, int64_t const start, int64_t const c
             int rcode = VSG_OK;
             fill_hit(h, S.qlen, a_score[a], a_al[a], a_ma[a], a_mi[a], a_ga[a], a_tr.data() + 4 * a, S.seqno, rcode);
             if (rcode != VSG_OK) { return rcode; }
-            if (acceptable_aligned(h, opt_id, opt_weak_id, *opts, S.qlen, set->h_len[static_cast<size_t>(h.target)])) { S.accepts++; } else { S.rejects++; }
+            if (acceptable_aligned(h, opt_id, opt_weak_id, *opts, S.qlen, set->h_len[static_cast<size_t>(h.target)], size_of(S.seqno), size_of(h.target))) { S.accepts++; } else { S.rejects++; }
             ++a;
           }
         }
@@ -439,7 +439,7 @@ int session_rounds(vsg_cluster_session & s, int64_t const start, int64_t const c
             }
           }
           if (!h.rejected) {
-            if (acceptable_aligned(h, opt_id, opt_weak_id, *opts, S.qlen, set->h_len[static_cast<size_t>(h.target)])) { ++S.accepts; } else { ++S.rejects; }
+            if (acceptable_aligned(h, opt_id, opt_weak_id, *opts, S.qlen, set->h_len[static_cast<size_t>(h.target)], size_of(S.seqno), size_of(h.target))) { ++S.accepts; } else { ++S.rejects; }
           }
         }
         size_t keep = S.hits.size();   // delete all undetermined hits from the first one on

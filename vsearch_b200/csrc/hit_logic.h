@@ -89,7 +89,8 @@ inline bool acceptable_unaligned(const vsg_search_opts & o, int qseqlen, int64_t
 }
 
 // search_acceptable_aligned (searchcore.cpp:664-737)
-inline bool acceptable_aligned(Hit & h, double opt_id, double opt_weak_id, const vsg_search_opts & o, int qseqlen, int dseqlen)
+inline bool acceptable_aligned(Hit & h, double opt_id, double opt_weak_id, const vsg_search_opts & o, int qseqlen, int dseqlen,
+                               int64_t qsize = 1, int64_t tsize = 1)
 {
   double const mid = 100.0 * h.matches / (h.matches + h.mismatches);  // 0/0 -> NaN fails the test, as in the reference
   if (h.id >= 100.0 * opt_weak_id && h.mismatches <= o.maxsubs && h.internal_gaps <= o.maxgaps &&
@@ -100,6 +101,12 @@ inline bool acceptable_aligned(Hit & h, double opt_id, double opt_weak_id, const
       (h.matches + h.mismatches >= o.query_cov * qseqlen) &&
       (h.matches + h.mismatches >= o.target_cov * static_cast<double>(dseqlen)) &&
       h.id <= 100.0 * o.maxid && mid >= o.mid && (h.mismatches + h.internal_indels <= o.maxdiffs)) {
+    if (o.unoise != 0) {   // searchcore.cpp:700-717
+      double const skew = 1.0 * static_cast<double>(qsize) / static_cast<double>(tsize);
+      double const beta = 1.0 / std::pow(2, (1.0 * o.unoise_alpha * h.mismatches) + 1);
+      if (skew <= beta || h.mismatches == 0) { h.accepted = true; h.weak = false; return true; }
+      h.rejected = true; h.weak = true; return false;
+    }
     if (h.id >= 100.0 * opt_id) { h.accepted = true; h.weak = false; return true; }
     h.rejected = true; h.weak = true; return false;
   }

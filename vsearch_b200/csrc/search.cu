@@ -112,7 +112,7 @@ extern "C" void vsg_search_opts_default(vsg_search_opts * o)
   o->maxsubs = 2147483647; o->maxgaps = 2147483647; o->mincols = 0; o->maxdiffs = 2147483647;
   o->leftjust = 0; o->rightjust = 0;
   o->maxqsize = INT64_MAX; o->mintsize = 0; o->minsizeratio = 0.0; o->maxsizeratio = 1.7976931348623157e308;
-  o->idprefix = 0; o->idsuffix = 0; o->self = 0; o->selfid = 0; o->qmask_dust = 0; o->reserved0 = 0;
+  o->idprefix = 0; o->idsuffix = 0; o->self = 0; o->selfid = 0; o->qmask_dust = 0; o->unoise = 0; o->unoise_alpha = 2.0;
   o->query_sizes = nullptr; o->target_sizes = nullptr; o->query_labels = nullptr; o->target_labels = nullptr;
 }
 
@@ -160,7 +160,8 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
     tb_gate = (e == nullptr || e[0] != '0') && !lazy && !c->sp.fallback &&
               opts->maxsubs == d.maxsubs && opts->maxgaps == d.maxgaps && opts->mincols == d.mincols && opts->maxdiffs == d.maxdiffs &&
               opts->leftjust == 0 && opts->rightjust == 0 && opts->query_cov == d.query_cov && opts->target_cov == d.target_cov &&
-              opts->maxid == d.maxid && opts->mid == d.mid && opts->iddef >= 0 && opts->iddef <= 4 && opt_weak_id <= opt_id;
+              opts->maxid == d.maxid && opts->mid == d.mid && opts->iddef >= 0 && opts->iddef <= 4 && opt_weak_id <= opt_id &&
+              opts->unoise == 0;
   }
   for (int64_t q = 0; q < nq; q++) { counts[q] = 0; }
   if (seqcount == 0 || nq == 0) { if (work) { work[0] = work[1] = work[2] = work[3] = 0; } return VSG_OK; }
@@ -586,7 +587,9 @@ extern "C" int vsg_search_batch(vsg_ctx * c, const vsg_index * ix, const vsg_seq
             h.matches = static_cast<int>(nal) - h.nwdiff;
             h.mismatches = h.nwdiff - h.nwindels;
             finish_hit(h, trims4, opts->iddef);
-            if (acceptable_aligned(h, opt_id, opt_weak_id, *opts, qlen, dlen)) { S.accepts++; } else { S.rejects++; }
+            int64_t const qsz = opts->query_sizes != nullptr ? opts->query_sizes[b0 + ql] : 1;
+            int64_t const tsz = opts->target_sizes != nullptr ? opts->target_sizes[h.target] : 1;
+            if (acceptable_aligned(h, opt_id, opt_weak_id, *opts, qlen, dlen, qsz, tsz)) { S.accepts++; } else { S.rejects++; }
             ++i;
           }
         }

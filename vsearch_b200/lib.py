@@ -42,9 +42,10 @@ class SearchOpts(C.Structure):
                 ("leftjust", C.c_int32), ("rightjust", C.c_int32),
                 ("maxqsize", C.c_int64), ("mintsize", C.c_int64), ("minsizeratio", C.c_double),
                 ("maxsizeratio", C.c_double), ("idprefix", C.c_int32), ("idsuffix", C.c_int32),
-                ("self", C.c_int32), ("selfid", C.c_int32), ("qmask_dust", C.c_int32), ("reserved0", C.c_int32),
+                ("self", C.c_int32), ("selfid", C.c_int32), ("qmask_dust", C.c_int32), ("unoise", C.c_int32),
                 ("query_sizes", C.POINTER(C.c_int64)), ("target_sizes", C.POINTER(C.c_int64)),
-                ("query_labels", C.POINTER(C.c_int64)), ("target_labels", C.POINTER(C.c_int64))]
+                ("query_labels", C.POINTER(C.c_int64)), ("target_labels", C.POINTER(C.c_int64)),
+                ("unoise_alpha", C.c_double)]
 
 
 class Profile(C.Structure):
