@@ -221,6 +221,10 @@ typedef struct vsg_search_opts {
   const int64_t * query_labels;  /* --self: label identities, [i] for query q0+i resp. [t] for target t; two  */
   const int64_t * target_labels; /*         sequences carry the same header iff their identities are equal  */
   double unoise_alpha;    /* --unoise_alpha (2.0) */
+  int32_t sizeorder;      /* --sizeorder (vsg_cluster_fast / sessions, with maxaccepts > 1): among the accepted hits the centroid of
+                             highest abundance wins, then identity, then the earlier one (search_findbest2_bysize,
+                             searchcore.cpp:182-240, 994-1025) instead of identity first; needs target_sizes */
+  int32_t reserved1;
 } vsg_search_opts;
 
 typedef struct vsg_search_result {

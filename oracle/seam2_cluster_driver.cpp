@@ -47,6 +47,7 @@ int main(int argc, char ** argv)
     else if (k == "maxqt") { p.opt_maxqt = std::atof(v); }
     else if (k == "mid") { p.opt_mid = std::atof(v); }
     else if (k == "unoise_alpha") { p.opt_cluster_unoise = const_cast<char *>("unoise"); p.opt_unoise_alpha = std::atof(v); }
+    else if (k == "sizeorder") { p.opt_sizeorder = std::atoi(v) != 0; }
     else if (k == "chunk") { chunk = std::atoi(v); }
     else { std::fprintf(stderr, "unknown key %s\n", k.c_str()); return 2; }
   }

@@ -182,7 +182,6 @@ auto cluster_session_init(struct cluster_session_s * cs, struct Parameters const
   cs->parameters = &p; cs->dbindex = &dbindex; cs->db = &db;
   cs->seqcount = static_cast<int>(db.getsequencecount());
   if (p.opt_strand) { fatal("GPU cluster session: --strand both is not offered on this path"); }
-  if (p.opt_sizeorder) { fatal("GPU cluster session: --sizeorder is not offered on this path"); }
 
   vsg_scoring sco;
   int64_t const v[14] = {p.opt_match, p.opt_mismatch,
@@ -226,6 +225,7 @@ auto cluster_session_init(struct cluster_session_s * cs, struct Parameters const
   o.maxsubs = p.opt_maxsubs; o.maxgaps = p.opt_maxgaps; o.mincols = p.opt_mincols; o.maxdiffs = p.opt_maxdiffs;
   o.leftjust = p.opt_leftjust != 0 ? 1 : 0; o.rightjust = p.opt_rightjust != 0 ? 1 : 0;
   o.unoise = (p.opt_cluster_unoise != nullptr) ? 1 : 0; o.unoise_alpha = p.opt_unoise_alpha;
+  o.sizeorder = p.opt_sizeorder ? 1 : 0;
   o.maxqsize = p.opt_maxqsize; o.mintsize = p.opt_mintsize;
   o.minsizeratio = p.opt_minsizeratio; o.maxsizeratio = p.opt_maxsizeratio;
   o.self = p.opt_self != 0 ? 1 : 0;

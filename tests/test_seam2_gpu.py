@@ -162,6 +162,7 @@ def _reads(tmp_path):
     ["id=0.97", "threads=4", "chunk=400", "minsl=0.9", "mid=0.9"],
     ["id=0.9", "threads=16", "chunk=300", "unoise_alpha=2.0"],   # --cluster_unoise acceptance: abundance skew instead of --id
     ["id=0.9", "threads=1", "chunk=0", "unoise_alpha=0.5", "maxaccepts=2"],
+    ["id=0.9", "threads=8", "chunk=0", "maxaccepts=4", "maxrejects=16", "sizeorder=1"],   # the most abundant accepted centroid wins
 ])
 def test_cluster_session_shim_equals_the_reference(tmp_path, case):
     reads = _reads(tmp_path)

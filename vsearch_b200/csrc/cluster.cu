@@ -448,7 +448,12 @@ int session_rounds(vsg_cluster_session & s, int64_t const start, int64_t const c
       }
       // search_findbest2_byid (searchcore.cpp:960-991): the first hit that no other one precedes in the by-id order
       const Hit * best = nullptr;
-      for (const Hit & h : S.hits) { if (best == nullptr || hit_less(h, *best)) { best = &h; } }
+      for (const Hit & h : S.hits) {
+        // --sizeorder: search_findbest2_bysize (searchcore.cpp:994-1025)
+        bool const better = best == nullptr ||
+                            (opts->sizeorder != 0 ? hit_less_bysize(h, *best, size_of(h.target), size_of(best->target)) : hit_less(h, *best));
+        if (better) { best = &h; }
+      }
       if (best != nullptr && !best->accepted) { best = nullptr; }
       vsg_cluster_result & r = results[static_cast<size_t>(S.seqno - start)];
       std::memset(&r, 0, sizeof r);

@@ -123,5 +123,15 @@ inline bool hit_less(const Hit & a, const Hit & b)
   return a.target < b.target;
 }
 
+// hit_compare_bysize (searchcore.cpp:182-240): abundance of the target first
+inline bool hit_less_bysize(const Hit & a, const Hit & b, int64_t a_size, int64_t b_size)
+{
+  if (a.rejected != b.rejected) { return a.rejected < b.rejected; }
+  if (a.aligned != b.aligned) { return a.aligned > b.aligned; }
+  if (!a.aligned) { return false; }
+  if (a_size != b_size) { return a_size > b_size; }
+  if (a.id != b.id) { return a.id > b.id; }
+  return a.target < b.target;
+}
 
 }  // namespace vsg

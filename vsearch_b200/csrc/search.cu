@@ -112,7 +112,7 @@ extern "C" void vsg_search_opts_default(vsg_search_opts * o)
   o->maxsubs = 2147483647; o->maxgaps = 2147483647; o->mincols = 0; o->maxdiffs = 2147483647;
   o->leftjust = 0; o->rightjust = 0;
   o->maxqsize = INT64_MAX; o->mintsize = 0; o->minsizeratio = 0.0; o->maxsizeratio = 1.7976931348623157e308;
-  o->idprefix = 0; o->idsuffix = 0; o->self = 0; o->selfid = 0; o->qmask_dust = 0; o->unoise = 0; o->unoise_alpha = 2.0;
+  o->idprefix = 0; o->idsuffix = 0; o->self = 0; o->selfid = 0; o->qmask_dust = 0; o->unoise = 0; o->unoise_alpha = 2.0; o->sizeorder = 0; o->reserved1 = 0;
   o->query_sizes = nullptr; o->target_sizes = nullptr; o->query_labels = nullptr; o->target_labels = nullptr;
 }
 

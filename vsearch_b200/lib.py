@@ -45,7 +45,7 @@ class SearchOpts(C.Structure):
                 ("self", C.c_int32), ("selfid", C.c_int32), ("qmask_dust", C.c_int32), ("unoise", C.c_int32),
                 ("query_sizes", C.POINTER(C.c_int64)), ("target_sizes", C.POINTER(C.c_int64)),
                 ("query_labels", C.POINTER(C.c_int64)), ("target_labels", C.POINTER(C.c_int64)),
-                ("unoise_alpha", C.c_double)]
+                ("unoise_alpha", C.c_double), ("sizeorder", C.c_int32), ("reserved1", C.c_int32)]
 
 
 class Profile(C.Structure):
