@@ -7,15 +7,17 @@
 //                                                                 threshold, best `tophits` targets
 //   minheap_*               (core/minheap.cpp:82-263)             order: count desc, length asc, seqno asc
 //
-// Layout.  The database is cut into SHARDS of at most 32768 consecutive targets.  A shard stores
-// CSR postings: start[4^k + 1] (u32) and post[] holding 15-bit shard-local target numbers as u16
-// (half the bytes of the reference's u32 lists; the reference's per-k-mer bitmaps for very frequent
-// k-mers, dbindex.cpp:212-229, are a storage variant with the same meaning and are not needed).
-// One CTA ranks one query: for every shard it zeroes 32768 16-bit counters in SHARED memory,
-// streams the postings of the query's distinct k-mers (coalesced u16 loads, one warp per list)
-// into them with shared-memory atomics, scans the counters against the threshold and appends the
-// survivors as 64-bit sort keys to a candidate list that is bitonic-sorted and cut to `tophits`
-// whenever it fills up and once at the end.  HBM traffic per query is the postings themselves
+// Layout.  The database is cut into SHARDS of at most 32766 consecutive targets (static index; 32768 for the cluster
+// driver's incremental one).  A shard stores CSR postings; in the static index every k-mer has two sub-lists, its even
+// and its odd targets, and a posting is the BYTE OFFSET of the target's counter word as a u16 (half the bytes of the
+// reference's u32 lists; the reference's per-k-mer bitmaps for very frequent k-mers, dbindex.cpp:212-229, are a storage
+// variant with the same meaning and are not needed).  --wordlength 3..10: list heads for all 2 * 4^k sub-lists;
+// 11..15: only the sub-lists that exist, found by binary search (build_sparse_shard).
+// One CTA ranks one query: for every shard it zeroes 32768 16-bit counters in SHARED memory, turns the postings of
+// the query's distinct k-mers into shared-memory atomic adds — the runs of all k-mers laid end to end as one stream
+// of 16-byte vectors that the 16 warps split evenly (every lane busy every round) —, scans the counters against a
+// running threshold and appends the survivors as 64-bit sort keys to a candidate list that is sorted and cut to
+// `tophits` at the end (and whenever a crowd of ties fills it up).  HBM traffic per query is the postings themselves
 // (2 B each) — the counters never leave the SM.
 #include "vsg_internal.h"
 
