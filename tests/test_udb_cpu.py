@@ -122,3 +122,26 @@ def test_invalid_udb_files_are_rejected(tmp_path):
     assert vlib.udb_detect(str(tmp_path / "bad.udb"))                               # the signature alone says UDB
     with pytest.raises(vlib.VsgError):
         vlib.Udb(str(tmp_path / "missing.udb"))
+
+
+@needs_stock
+def test_c_example_builds_and_parses_a_udb_file(tmp_path):
+    """examples/usearch_udb.c (plain C against include/vsg.h) compiles with gcc, links libvsg.so, reads a UDB file made by
+    the reference and — in a container without a GPU — stops at the first device call with the library's error message
+    instead of falling back to anything"""
+    fasta, seqs = make_db(tmp_path, n=30)
+    udb = str(tmp_path / "db.udb")
+    makeudb(fasta, udb)
+    exe = str(tmp_path / "usearch_udb")
+    csrc = os.path.join(ROOT, "vsearch_b200", "csrc")
+    r = subprocess.run(["gcc", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "usearch_udb.c"), "-L", csrc, "-lvsg", f"-Wl,-rpath,{csrc}", "-o", exe],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, udb, fasta, str(tmp_path / "out.b6"), "0.9"], capture_output=True, text=True, timeout=300)
+    assert f"{len(seqs)} sequences" in r.stderr and "word length 8" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        assert r.returncode == 1 and "vsg_group_create_udb" in r.stderr
+    else:
+        assert r.returncode == 0, r.stderr
