@@ -149,3 +149,32 @@ def test_topscores_and_search_match_reference():
             assert got == ref_rows[i], (i, got, ref_rows[i])
         o.close()
         r.close()
+
+
+@pytest.mark.parametrize("k", [10, 11, 13, 14])
+def test_large_wordlengths_match_reference(k):
+    """k >= 10 is the reference's hash variant of unique_count (unique.cpp:243-334); from 13 on the oracle keeps its
+    index as sorted (k-mer, target) pairs instead of 4^k list heads: candidate lists and whole searches still equal
+    the reference's, soft-masked and IUPAC symbols included"""
+    rng = np.random.default_rng(100 + k)
+    db, roots = _family_db(rng)
+    r = _libs.RefDb(db, k=k, id=0.9, maxaccepts=2, maxrejects=16)
+    o = _libs.OracleDb(db, k=k)
+    opts = _libs.search_opts(len(db), id=0.9, maxaccepts=2, maxrejects=16, k=k)
+    assert opts.tophits == r.tophits
+    qs = [synth.mutate(rng, roots[i % roots.shape[0]], 0.05).tobytes()[: int(rng.integers(60, 300))] for i in range(30)]
+    qs += [b"ACGTACGTAC", synth.random_seqs(rng, 1, 200)[0].tobytes(), roots[0].tobytes()[:120] + b"NNRY" + roots[0].tobytes()[124:200]]
+    ref_rows = r.search(synth.SeqSet(qs), max_results=opts.tophits)
+    nonempty = 0
+    for i, q in enumerate(qs):
+        for m in (0, 1):
+            assert np.array_equal(_libs.oracle_unique_kmers(q, k, m), _libs.ref_unique_kmers(q, k, m)), (k, i, m)
+        s1, c1 = r.topscores(q)
+        s2, c2 = o.topscores(q, opts)
+        assert np.array_equal(s1, s2) and np.array_equal(c1, c2), (k, i)
+        nonempty += len(s1) > 0
+        hits, _, _ = o.search(q, opts)
+        got = [(h.target, h.id, h.matches, h.mismatches, h.nwgaps, h.nwalignmentlength, h.accepted, h.strand) for h in hits]
+        assert got == ref_rows[i], (k, i)
+    assert nonempty >= 25
+    o.close(); r.close()
